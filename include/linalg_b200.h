@@ -1,0 +1,127 @@
+/* linalg_b200 -- C ABI of the B200-native dense-factorisation hot path.
+ *
+ * Drop-in boundary for BrantleighBunting/linalg's QR / least-squares / A^T A-SVD path.
+ * The reference has no FFI of its own (pure Python + NumPy); each entry
+ * point below replaces the Python function cited next to it, which the reference-side ctypes
+ * stub in INTEGRATION.md binds 1:1.
+ *
+ * Conventions
+ *   - all matrices are float64, row-major (C order), densely packed; batched arrays are
+ *     (batch, rows, cols) with the batch index slowest -- exactly a C-contiguous NumPy array.
+ *   - return value: 0 ok; < 0 argument / shape error (Python shim raises ValueError);
+ *     > 0 CUDA (1000 + cudaError_t) or NCCL (5000 + ncclResult_t) failure (RuntimeError).
+ *     lq_last_error() gives the text.  There is NO CPU fallback anywhere in this library.
+ *   - "_dev" entry points take DEVICE pointers and enqueue on the context's stream without
+ *     synchronising; the plain entry points take HOST pointers, copy in, run, copy out and
+ *     return when the outputs are complete.
+ *   - a context owns one device, one stream, its scratch memory and (optionally) one NCCL
+ *     communicator; calls on one context must be serialised by the caller.
+ *   - data-dependent failures (a linearly dependent column in MGS, linalg/qr.py:40-41) are
+ *     reported per matrix in info[] (0 = fine, j+1 = first failing column); the shim raises
+ *     the reference's ValueError.
+ */
+#ifndef LINALG_B200_H_
+#define LINALG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lq_ctx lq_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+const char* lq_version(void);
+int lq_device_count(int* count);
+int lq_create(int device, lq_ctx** out);
+int lq_destroy(lq_ctx* ctx);
+const char* lq_last_error(lq_ctx* ctx); /* ctx may be NULL: last error of a failed lq_create */
+/* props[0]=SM count, [1]=cc major, [2]=cc minor, [3]=max dyn smem per block, [4]=SM clock kHz,
+ * [5]=total global memory MiB, [6]=L2 bytes, [7]=max cluster size usable by the panel kernel */
+int lq_device_props(lq_ctx* ctx, int64_t props[8]);
+
+/* ---- memory / stream / timing ------------------------------------------------------------ */
+int lq_malloc(lq_ctx* ctx, size_t bytes, void** dptr);
+int lq_free(lq_ctx* ctx, void* dptr);
+int lq_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
+int lq_host_free(void* hptr);
+int lq_memcpy_h2d(lq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int lq_memcpy_d2h(lq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int lq_memcpy_d2d(lq_ctx* ctx, void* dst, const void* src, size_t bytes);
+int lq_memset(lq_ctx* ctx, void* dst, int value, size_t bytes);
+int lq_sync(lq_ctx* ctx);
+int lq_event_record(lq_ctx* ctx, int slot);                       /* slot 0..15, on ctx stream */
+int lq_event_elapsed_ms(lq_ctx* ctx, int slot_a, int slot_b, float* ms); /* syncs on slot_b */
+int lq_flush_l2(lq_ctx* ctx);        /* overwrite a 256 MiB scratch buffer (> 126 MB L2) */
+int64_t lq_kernel_launches(lq_ctx* ctx); /* number of this library's kernels launched so far */
+
+/* ---- a1: householder_qr  (linalg/qr.py:52-100) ------------------------------------------- */
+/* A (batch, m, n) -> Q (batch, m, n), R (batch, n, n); requires m >= n >= 1.
+ * variant: 0 = library default; other values select a specific kernel (bench/tests). */
+int lq_householder_qr_batched_dev(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, double* Q, double* R,
+                                  int variant);
+int lq_householder_qr_batched(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, double* Q, double* R);
+/* single (possibly large) matrix: blocked compact-WY Householder */
+int lq_householder_qr_dev(lq_ctx* ctx, const double* A, int m, int n, double* Q, double* R);
+int lq_householder_qr(lq_ctx* ctx, const double* A, int m, int n, double* Q, double* R);
+
+/* ---- a2: qr = modified Gram-Schmidt  (linalg/qr.py:14-49) --------------------------------- */
+int lq_mgs_qr_batched_dev(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, int reorth, double* Q,
+                          double* R, int32_t* info);
+int lq_mgs_qr_batched(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, int reorth, double* Q, double* R,
+                      int32_t* info);
+int lq_mgs_qr_dev(lq_ctx* ctx, const double* A, int m, int n, int reorth, double* Q, double* R, int32_t* info);
+int lq_mgs_qr(lq_ctx* ctx, const double* A, int m, int n, int reorth, double* Q, double* R, int32_t* info);
+
+/* ---- a3: least_squares_householder_qr  (linalg/qr.py:122-134) ------------------------------ */
+/* A (batch, m, n), B (batch, m, nrhs) -> X (batch, n, nrhs) */
+int lq_lstsq_householder_batched_dev(lq_ctx* ctx, const double* A, const double* B, int64_t batch, int m, int n,
+                                     int nrhs, double* X);
+int lq_lstsq_householder_batched(lq_ctx* ctx, const double* A, const double* B, int64_t batch, int m, int n,
+                                 int nrhs, double* X);
+
+/* ---- a4: least_squares_qr (MGS)  (linalg/qr.py:103-119) ------------------------------------ */
+int lq_lstsq_mgs_batched_dev(lq_ctx* ctx, const double* A, const double* B, int64_t batch, int m, int n, int nrhs,
+                             double* X, int32_t* info);
+int lq_lstsq_mgs_batched(lq_ctx* ctx, const double* A, const double* B, int64_t batch, int m, int n, int nrhs,
+                         double* X, int32_t* info);
+
+/* ---- a5: svd via the A^T A eigen-route  (linalg/svd.py:10-82), m >= n ------------------------- */
+/* U (m, n), s (n) descending, Vt (n, n); *rank = #(s > tol).  Columns of U beyond rank are
+ * left ZERO here; the shim completes them (svd.py:67-76) with lq_householder_qr. */
+int lq_svd_gram_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
+                    int* rank_host);
+int lq_svd_gram(lq_ctx* ctx, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
+                int* rank_host);
+/* building blocks (device pointers) */
+int lq_gram_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double* G);          /* G = A^T A (n x n) */
+int lq_eigh_dev(lq_ctx* ctx, const double* G, int n, double* lambda_desc, double* V); /* Jacobi; columns of V */
+int lq_gemm_dev(lq_ctx* ctx, int transa, int transb, int64_t m, int n, int k, double alpha, const double* A,
+                int lda, const double* B, int ldb, double beta, double* C, int ldc); /* row-major C = a op(A) op(B) + b C */
+
+/* ---- a7: TSQR for tall-skinny matrices, diag(R) > 0 (the MGS convention) ------------------------ */
+int lq_tsqr_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double* Q, double* R);
+int lq_tsqr(lq_ctx* ctx, const double* A, int64_t m, int n, double* Q, double* R);
+
+/* ---- multi-GPU: one process (context) per GPU, NCCL over NVLink ---------------------------------- */
+int lq_comm_unique_id(void* id128);                                     /* 128 bytes, from rank 0 */
+int lq_comm_init(lq_ctx* ctx, int nranks, int rank, const void* id128); /* collective */
+int lq_comm_destroy(lq_ctx* ctx);
+int lq_comm_allreduce_sum(lq_ctx* ctx, double* dbuf, int64_t count);    /* in place, ctx stream */
+int lq_comm_allgather(lq_ctx* ctx, const double* dsend, double* drecv, int64_t count_per_rank);
+/* row-sharded: every rank passes its (m_local, n) block; R / s / Vt are replicated */
+int lq_tsqr_sharded_dev(lq_ctx* ctx, const double* A_local, int64_t m_local, int n, double* Q_local, double* R);
+int lq_svd_gram_sharded_dev(lq_ctx* ctx, const double* A_local, int64_t m_local, int n, double tol, double* U_local,
+                            double* s, double* Vt, int* rank_host);
+
+/* ---- roofline probes (bench.py) --------------------------------------------------------------------- */
+/* kind 0: FP64 FMA (DFMA) peak, 1: FP64 tensor (DMMA m16n8k8) peak, 2: device copy GB/s.
+ * result in TFLOP/s (kinds 0,1) or GB/s (kind 2). */
+int lq_probe(lq_ctx* ctx, int kind, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINALG_B200_H_ */

@@ -1,0 +1,66 @@
+// Context object behind the opaque lq_ctx handle.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct lq_ctx {};  // opaque tag for the C ABI
+
+namespace lq {
+
+struct Ctx : lq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t lane[2] = {nullptr, nullptr};  // copy/compute lanes of the host-pointer pipelines
+    cudaEvent_t ev[16] = {};
+    cudaDeviceProp prop{};
+    int sm_count = 0;
+    int max_smem = 0;        // opt-in dynamic shared memory per block
+    int max_cluster = 1;     // largest cluster size the panel kernel may use
+    std::string err;
+    void* flush_buf = nullptr;
+    long long launches = 0;
+    // NCCL (loaded lazily with dlopen)
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+std::string& global_error();
+
+inline Ctx* as_ctx(lq_ctx* c) { return static_cast<Ctx*>(c); }
+
+// stream-ordered scratch buffer (cudaMallocAsync pool; no host synchronisation after warm-up)
+struct DevBuf {
+    Ctx* ctx = nullptr;
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int alloc(Ctx* c, size_t bytes, cudaStream_t stream = nullptr) {
+        release();
+        ctx = c;
+        s = stream ? stream : c->stream;
+        if (bytes == 0) bytes = 16;
+        LQ_CUDA(c, cudaMallocAsync(&p, bytes, s));
+        return LQ_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+#define LQ_COUNT_LAUNCH(ctx) ((ctx)->launches++)
+
+}  // namespace lq
