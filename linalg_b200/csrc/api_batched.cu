@@ -10,10 +10,10 @@
 namespace lq {
 
 // ------------------------------------------------------------------ 32x32 fast kernels
-template <int P, int C, int WARPS, bool KEEPV, int MINB>
+template <int P, int C, int WARPS, bool KEEPV, int MINB, int NR = 3>
 static int launch_hh32(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
     using D = Dist32<P, C>;
-    auto kern = hh_qr32_kernel<P, C, WARPS, KEEPV, MINB>;
+    auto kern = hh_qr32_kernel<P, C, WARPS, KEEPV, MINB, NR>;
     const size_t smem = (size_t)WARPS * D::MPW * D::SMEM_DOUBLES * sizeof(double);
     static bool configured[64] = {};
     if (!configured[c->device]) {
@@ -48,15 +48,18 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
     if (m == 32 && n == 32 && variant >= 0) {
         switch (variant) {
             case 0:
-            case 4: return launch_hh32<2, 4, 2, false, 6>(c, st, A, batch, Q, R);
+            case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
             case 2: return launch_hh32<1, 2, 4, false, 2>(c, st, A, batch, Q, R);
-            case 3: return launch_hh32<2, 2, 4, false, 3>(c, st, A, batch, Q, R);
-            case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
-            case 6: return launch_hh32<2, 4, 1, false, 12>(c, st, A, batch, Q, R);
-            case 7: return launch_hh32<2, 4, 4, false, 3>(c, st, A, batch, Q, R);
-            case 8: return launch_hh32<2, 4, 2, false, 5>(c, st, A, batch, Q, R);
-            case 9: return launch_hh32<2, 2, 4, false, 4>(c, st, A, batch, Q, R);
+            case 3: return launch_hh32<2, 2, 4, false, 4>(c, st, A, batch, Q, R);
+            case 4: return launch_hh32<2, 4, 2, false, 5>(c, st, A, batch, Q, R);
+            case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);
+            case 7: return launch_hh32<2, 4, 1, true, 8>(c, st, A, batch, Q, R);
+            case 8: return launch_hh32<4, 4, 4, true, 4>(c, st, A, batch, Q, R);
+            case 9: return launch_hh32<4, 4, 4, true, 3>(c, st, A, batch, Q, R);
+            case 10: return launch_hh32<4, 4, 4, false, 5>(c, st, A, batch, Q, R);
+            case 11: return launch_hh32<2, 2, 4, true, 3>(c, st, A, batch, Q, R);
+            case 12: return launch_hh32<4, 4, 2, true, 8, 2>(c, st, A, batch, Q, R);
             default: break;
         }
         set_error(c, "householder_qr_batched: unknown kernel variant %d", variant);

@@ -103,6 +103,56 @@ __global__ void __launch_bounds__(256) probe_copy_kernel(const double4* __restri
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) dst[i] = src[i];
 }
+// latency of a dependent DFMA chain (cycles per DFMA), one warp
+__global__ void probe_dfma_latency_kernel(double* out, double seed) {
+    double a = seed;
+    const double m = 1.0000001, c = 1e-9;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+#pragma unroll
+        for (int u = 0; u < 64; ++u) a = fma(a, m, c);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) {
+        out[0] = (double)(t1 - t0) / (64.0 * 64.0);
+        out[1] = a;
+    }
+}
+// accuracy of the MUFU seeds and of the Newton-refined reciprocal / rsqrt / sqrt used by the kernels
+__global__ void probe_seed_accuracy_kernel(double* out) {
+    double e_rcp = 0, e_rsq = 0, e_rcp_nr = 0, e_rsq_nr = 0, e_sqrt_nr = 0, e_rcp2 = 0, e_rsq2 = 0;
+    unsigned long long st = 0x9E3779B97F4A7C15ull * (threadIdx.x + 1 + 1024ull * blockIdx.x);
+    for (int it = 0; it < 4096; ++it) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const double u = (double)(st >> 11) * (1.0 / 9007199254740992.0);
+        const int ex = (int)((st >> 3) % 40) - 20;
+        const double x = ldexp(0.5 + u, ex * 3);
+        const double r_true = 1.0 / x, q_true = 1.0 / sqrt(x);
+        e_rcp = fmax(e_rcp, fabs(rcp_seed(x) - r_true) / r_true);
+        e_rsq = fmax(e_rsq, fabs(rsqrt_seed(x) - q_true) / q_true);
+        e_rcp_nr = fmax(e_rcp_nr, fabs(rcp_nr(x) - r_true) / r_true);
+        e_rsq_nr = fmax(e_rsq_nr, fabs(rsqrt_nr(x) - q_true) / q_true);
+        double ri;
+        e_sqrt_nr = fmax(e_sqrt_nr, fabs(sqrt_nr(x, ri) - sqrt(x)) / sqrt(x));
+        {   // two Newton steps only
+            double y = rcp_seed(x);
+            double e = fma(-x, y, 1.0); y = fma(y, e, y);
+            e = fma(-x, y, 1.0); y = fma(y, e, y);
+            e_rcp2 = fmax(e_rcp2, fabs(y - r_true) / r_true);
+            double z = rsqrt_seed(x); const double hx = 0.5 * x;
+            double f = fma(-hx * z, z, 0.5); z = fma(z, f, z);
+            f = fma(-hx * z, z, 0.5); z = fma(z, f, z);
+            e_rsq2 = fmax(e_rsq2, fabs(z - q_true) / q_true);
+        }
+    }
+    double v[7] = {e_rcp, e_rsq, e_rcp_nr, e_rsq_nr, e_sqrt_nr, e_rcp2, e_rsq2};
+    for (int k = 0; k < 7; ++k) {
+        double m = v[k];
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)&out[k], (unsigned long long)__double_as_longlong(m));
+    }
+}
 __global__ void fill_kernel(double* p, size_t n, double v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -334,6 +384,29 @@ int lq_probe(lq_ctx* h, int kind, double* result) {
             if (rep > 0 && ms < best) best = ms;
         }
         *result = 2.0 * bytes / (best * 1e-3) / 1e9;
+        return LQ_OK;
+    }
+    if (kind == 4) {  // DFMA dependent-issue latency in cycles
+        DevBuf out;
+        LQ_TRY(out.alloc(c, 64));
+        probe_dfma_latency_kernel<<<1, 32, 0, c->stream>>>(out.as<double>(), 1.0);
+        LQ_CHECK_LAUNCH(c);
+        double hres[2];
+        LQ_CUDA(c, cudaMemcpyAsync(hres, out.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        *result = hres[0];
+        return LQ_OK;
+    }
+    if (kind >= 10 && kind < 17) {  // seed / Newton accuracy (max relative error), see probe_seed_accuracy_kernel
+        DevBuf out;
+        LQ_TRY(out.alloc(c, 64));
+        LQ_CUDA(c, cudaMemsetAsync(out.p, 0, 64, c->stream));
+        probe_seed_accuracy_kernel<<<8, 128, 0, c->stream>>>(out.as<double>());
+        LQ_CHECK_LAUNCH(c);
+        double hres[8];
+        LQ_CUDA(c, cudaMemcpyAsync(hres, out.p, 56, cudaMemcpyDeviceToHost, c->stream));
+        LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        *result = hres[kind - 10];
         return LQ_OK;
     }
     set_error(c, "lq_probe: unknown kind %d", kind);

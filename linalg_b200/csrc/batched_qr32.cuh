@@ -28,8 +28,12 @@ struct Dist32 {
     static constexpr int MPW = 32 / L;  // matrices per warp
     static constexpr int RPL = N / P;   // rows per lane
     static_assert(L <= 32 && L >= 1 && (L & (L - 1)) == 0, "bad distribution");
-    // per-matrix shared scratch: 32 reflector rows (dense) + beta[32] + v0[32]
-    static constexpr int SMEM_DOUBLES = N * N + 2 * N;
+    // per-matrix shared scratch: 32 reflector rows + beta[32] + v0[32].  Row lanes (p) and the
+    // matrices of a warp are staggered by 4 banks so that the broadcast 16-byte loads of the
+    // different (matrix, p) groups of one warp never collide.
+    static constexpr int PSTRIDE = RPL + (P > 1 ? 2 : 0);   // doubles between the p sub-rows
+    static constexpr int ROWP = P * PSTRIDE;                // doubles per reflector row
+    static constexpr int SMEM_DOUBLES = N * ROWP + 2 * N + 4;
     __device__ __host__ static constexpr int col(int s, int lc) {
         return (s & 1) ? ((s + 1) * LC - 1 - lc) : (s * LC + lc);
     }
@@ -50,7 +54,7 @@ __device__ __forceinline__ double group_sum(double v) {
 // ---------------------------------------------------------------------------------------------
 // Householder QR.  grid: ceil(batch / (WARPS * MPW)) blocks of WARPS warps.
 // ---------------------------------------------------------------------------------------------
-template <int P, int C, int WARPS, bool KEEPV, int MINB>
+template <int P, int C, int WARPS, bool KEEPV, int MINB, int NR>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     hh_qr32_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, long long batch) {
     using D = Dist32<P, C>;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     const long long matc = valid ? mat : (batch - 1);
 
     double* vb = smem + (size_t)(warp * D::MPW + g) * D::SMEM_DOUBLES;
-    double* betas = vb + N * N;
+    double* betas = vb + N * D::ROWP;
     double* v0s = betas + N;
 
     int colv[C];
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int so = D::owner_slot(j), lo = D::owner_lc(j);
         const int iib = j / P, jp = j % P;
         const int ii0 = iib & ~1;  // 16-byte aligned start for the paired loops
-        double* vj = vb + j * N + p * RPL;
+        double* vj = vb + j * D::ROWP + p * D::PSTRIDE;
 
         // owner lanes (both row parities) publish x = R[j:, j]
         if (lc == lo) {
@@ -97,11 +101,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         }
         __syncwarp();
 
-        // partial dots over rows >= j (row j enters with the raw pivot x0)
-        double d[C];
+        // partial dots over rows >= j (row j enters with the raw pivot x0); two accumulators per
+        // column slot shorten the dependent DFMA chains
+        double d[C], d2[C];
         double vkeep[KEEPV ? RPL : 2];
 #pragma unroll
-        for (int s = 0; s < C; ++s) d[s] = 0.0;
+        for (int s = 0; s < C; ++s) d[s] = 0.0, d2[s] = 0.0;
 #pragma unroll
         for (int ii = ii0; ii < RPL; ii += 2) {
             double2 vv = *reinterpret_cast<const double2*>(vj + ii);
@@ -115,32 +120,34 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
             for (int s = so; s < C; ++s) {
                 d[s] = fma(vv.x, r[s][ii], d[s]);
-                d[s] = fma(vv.y, r[s][ii + 1], d[s]);
+                d2[s] = fma(vv.y, r[s][ii + 1], d2[s]);
             }
         }
+#pragma unroll
+        for (int s = so; s < C; ++s) d[s] += d2[s];
         // sum of squares of x = the owner column's own dot product
         double ss = group_sum<P, C>(d[so]);
         ss = __shfl_sync(0xffffffffu, ss, lo, L);
-        const double x0 = vb[j * N + jp * RPL + iib];
+        const double x0 = vb[j * D::ROWP + jp * D::PSTRIDE + iib];
 
         double rinv;
         const double ssc = fmax(ss, 1e-300);
-        const double nrm = sqrt_nr(ssc, rinv);
+        const double nrm = sqrt_nr_t<NR>(ssc, rinv);
         const bool skip = nrm < kEps;  // qr.py:79-80
         const double alpha = copysign(nrm, x0);
         const double v0 = x0 + alpha;
-        const double beta = skip ? 0.0 : rcp_nr(nrm * fabs(v0));  // 2 / v^T v
+        const double beta = skip ? 0.0 : rcp_nr_t<NR>(nrm * fabs(v0));  // 2 / v^T v
         if (lm == 0) {
             betas[j] = beta;
             v0s[j] = v0;
         }
         const bool piv = (p == jp);
+        const double alpha_m = piv ? alpha : 0.0;
 
 #pragma unroll
         for (int s = so; s < C; ++s) {
             // v^T R[:, c] = x^T R[:, c] + alpha * R[j, c]
-            double part = d[s] + (piv ? alpha * r[s][iib] : 0.0);
-            part = group_sum<P, C>(part);
+            const double part = group_sum<P, C>(fma(alpha_m, r[s][iib], d[s]));
             d[s] = beta * part;
         }
         // R[j:, c] -= s_c v
@@ -193,15 +200,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int so = D::owner_slot(j);
         const int iib = j / P, jp = j % P;
         const int ii0 = iib & ~1;
-        const double* vj = vb + j * N + p * RPL;
+        const double* vj = vb + j * D::ROWP + p * D::PSTRIDE;
         const double beta = betas[j];
         const double v0 = v0s[j];
         const bool piv = (p == jp);
 
-        double d[C];
+        double d[C], d2[C];
         double vkeep[KEEPV ? RPL : 2];
 #pragma unroll
-        for (int s = 0; s < C; ++s) d[s] = 0.0;
+        for (int s = 0; s < C; ++s) d[s] = 0.0, d2[s] = 0.0;
 #pragma unroll
         for (int ii = ii0; ii < RPL; ii += 2) {
             double2 vv = *reinterpret_cast<const double2*>(vj + ii);
@@ -215,9 +222,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
             for (int s = so; s < C; ++s) {
                 d[s] = fma(vv.x, q[s][ii], d[s]);
-                d[s] = fma(vv.y, q[s][ii + 1], d[s]);
+                d2[s] = fma(vv.y, q[s][ii + 1], d2[s]);
             }
         }
+#pragma unroll
+        for (int s = so; s < C; ++s) d[s] += d2[s];
 #pragma unroll
         for (int s = so; s < C; ++s) d[s] = beta * group_sum<P, C>(d[s]);
 #pragma unroll

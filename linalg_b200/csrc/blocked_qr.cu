@@ -1,0 +1,494 @@
+// K4: blocked compact-WY Householder QR of one (possibly large) matrix -- linalg/qr.py:52-100.
+//
+// Two-level right-looking factorisation.  Outer block NB = 128 columns; inside it, 32-column
+// panels are factored by the register/DSMEM cluster kernel (panel.cuh), the rest of the outer
+// block is updated with the panel's own T, then the 128-wide block reflector I - V T V^T
+// (T from the Gram matrix V^T V) updates the trailing matrix with three FP64 tensor-core GEMMs:
+//     W  = V^T C          (TN, K = rows)
+//     W2 = T^T W          (TN, K = 128)
+//     C -= V W2           (NN, K = 128)
+// Q is formed by applying the block reflectors to the identity in reverse order.  The working
+// copies are padded to a multiple of 32 columns (zero columns are "skipped" reflectors, exactly
+// the reference's  ||x|| < 1e-12  branch), so every GEMM operand is 16-byte aligned.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/linalg_b200.h"
+#include "ops.cuh"
+#include "panel.cuh"
+
+namespace lq {
+
+namespace {
+
+constexpr int NB_OUT = 128;
+constexpr int NB_IN = 32;
+
+// ------------------------------------------------------------------ small helper kernels
+__global__ void __launch_bounds__(256) pad_copy_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst,
+                                                       int ldd, long long rows, int cols_src, int cols_dst) {
+    const long long total = rows * cols_dst;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cols_dst;
+        const int j = (int)(e - i * cols_dst);
+        dst[i * ldd + j] = (j < cols_src) ? src[i * lds + j] : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) unpad_copy_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst,
+                                                         int ldd, long long rows, int cols) {
+    const long long total = rows * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cols;
+        const int j = (int)(e - i * cols);
+        dst[i * ldd + j] = src[i * lds + j];
+    }
+}
+__global__ void __launch_bounds__(256) extract_upper_kernel(const double* __restrict__ src, int lds, double* __restrict__ R,
+                                                            int n) {
+    const long long total = (long long)n * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e - (long long)i * n);
+        R[e] = (j >= i) ? src[(long long)i * lds + j] : 0.0;  // strict lower triangle exact zeros (qr.py:97)
+    }
+}
+__global__ void __launch_bounds__(256) set_identity_kernel(double* __restrict__ Q, int ldq, long long rows, int cols) {
+    const long long total = rows * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / cols;
+        const int j = (int)(e - i * cols);
+        Q[i * ldq + j] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+// T (kb x kb upper, row-major ldt) from the Gram matrix G = V^T V of unit-norm reflectors:
+//   tau_j = 2 (0 for a skipped, i.e. zero, reflector);  T[j][j] = tau_j;
+//   T[0:j, j] = -tau_j * T[0:j, 0:j] * G[0:j, j]                          (LAPACK dlarft, forward/columnwise)
+__global__ void __launch_bounds__(128) larft_from_gram_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T,
+                                                              int ldt, int kb) {
+    extern __shared__ double sh[];
+    double* Ts = sh;                      // Ts[k * 129 + i] = T[i][k]
+    double* gcol = sh + 128 * 129;        // 128
+    const int i = threadIdx.x;
+    for (int e = i; e < 128 * 129; e += blockDim.x) Ts[e] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < kb; ++j) {
+        if (i < kb) gcol[i] = G[(long long)i * ldg + j];
+        __syncthreads();
+        const double tau = (gcol[j] > 0.5) ? 2.0 : 0.0;
+        double acc = 0.0;
+        if (i < j) {
+            for (int k = i; k < j; ++k) acc = fma(Ts[k * 129 + i], gcol[k], acc);
+        }
+        __syncthreads();
+        if (i < j) Ts[j * 129 + i] = -tau * acc;
+        if (i == j) Ts[j * 129 + i] = tau;
+        __syncthreads();
+    }
+    for (int e = i; e < kb * kb; e += blockDim.x) {
+        const int r = e / kb, c = e - r * kb;
+        T[(long long)r * ldt + c] = Ts[c * 129 + r];
+    }
+}
+
+// ------------------------------------------------------------------ generic (any height) panel, BLAS-2, multi-launch
+// Used only when the panel does not fit the cluster kernel (mp > 16 * 512 rows).  Column j:
+//   k1: per-CTA partial  x^T P[:, c]  for all c -> atomicAdd into acc[0:nb]; pivot row copied to acc[nb:2nb]
+//   k2: every CTA forms alpha, v0, beta and updates its rows; CTA 0 also maintains T_u, beta, v0, rdiag
+struct GPanelState {
+    double acc[64];     // [0:32) dots, [32:64) pivot row
+    double Tt[32 * 32]; // Tt[k*32+i] = T_u[i][k]
+    double beta[32], v0[32], rdiag[32];
+};
+__global__ void __launch_bounds__(256) gpanel_dots_kernel(const double* __restrict__ A, int lda, int mp, int nb, int j,
+                                                          GPanelState* st, int rows_per_cta) {
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(mp, r0 + rows_per_cta);
+    double d = 0.0;
+    for (int r = max(r0, j) + w; r < r1; r += 8) {
+        const double x = A[(long long)r * lda + j];
+        if (lane < nb) d = fma(x, A[(long long)r * lda + lane], d);
+    }
+    red[w][lane] = d;
+    __syncthreads();
+    if (w == 0) {
+        double s = 0.0;
+        for (int ww = 0; ww < 8; ++ww) s += red[ww][lane];
+        if (lane < nb && s != 0.0) atomicAdd(&st->acc[lane], s);
+        if (j >= r0 && j < r1 && lane < nb) st->acc[32 + lane] = A[(long long)j * lda + lane];
+    }
+}
+__global__ void __launch_bounds__(256) gpanel_update_kernel(double* __restrict__ A, int lda, int mp, int nb, int j,
+                                                            GPanelState* st, int rows_per_cta) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(mp, r0 + rows_per_cta);
+    const double tot = (lane < nb) ? st->acc[lane] : 0.0;
+    const double prow = (lane < nb && j < mp) ? st->acc[32 + lane] : 0.0;
+    const double ss = __shfl_sync(0xffffffffu, tot, j);
+    const double x0 = __shfl_sync(0xffffffffu, prow, j);
+    const double nrm = sqrt(fmax(ss, 0.0));
+    const bool skip = nrm < kEps;
+    const double alpha = copysign(nrm, x0);
+    const double v0 = x0 + alpha;
+    const double beta = skip ? 0.0 : 1.0 / (nrm * fabs(v0));
+    const double gl = fma(alpha, prow, tot);
+    const double sc = (lane > j && lane < nb) ? beta * gl : 0.0;
+    for (int r = max(r0, j) + w; r < r1; r += 8) {
+        double x = A[(long long)r * lda + j];
+        if (r == j) x = v0;
+        if (lane > j && lane < nb) A[(long long)r * lda + lane] = fma(-sc, x, A[(long long)r * lda + lane]);
+    }
+    if (blockIdx.x == 0 && w == 0) {
+        // T column (same recurrence as the cluster kernel) -- uses the totals before they are cleared
+        double acc = 0.0;
+        __shared__ double gb[32];
+        gb[lane] = gl;
+        __syncwarp();
+        for (int k = 0; k < j; ++k) acc = fma(st->Tt[k * 32 + lane], gb[k], acc);
+        if (lane < j) st->Tt[j * 32 + lane] = -beta * acc;
+        if (lane == j) st->Tt[j * 32 + lane] = beta;
+        if (lane == 0) {
+            st->beta[j] = beta;
+            st->v0[j] = v0;
+            st->rdiag[j] = skip ? x0 : -alpha;
+        }
+    }
+}
+__global__ void __launch_bounds__(64) gpanel_clear_kernel(GPanelState* st, int all) {
+    const int t = threadIdx.x;
+    st->acc[t] = 0.0;
+    if (all) {
+        for (int e = t; e < 32 * 32; e += 64) st->Tt[e] = 0.0;
+        if (t < 32) st->beta[t] = 0.0, st->v0[t] = 0.0, st->rdiag[t] = 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) gpanel_store_kernel(double* __restrict__ A, int lda, double* __restrict__ V, int ldv,
+                                                           double* __restrict__ T, int ldt, int mp, int nb,
+                                                           const GPanelState* st) {
+    const long long total = (long long)mp * nb;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / nb), c = (int)(e - (long long)row * nb);
+        const double bt = st->beta[c];
+        const double rn = sqrt(0.5 * bt);
+        double vv;
+        if (row > c) vv = A[(long long)row * lda + c] * rn;
+        else if (row == c) vv = st->v0[c] * rn;
+        else vv = 0.0;
+        V[(long long)row * ldv + c] = vv;
+        if (row == c) A[(long long)row * lda + c] = st->rdiag[c];
+    }
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+            const int i = e / nb, k = e - i * nb;
+            const double bi = st->beta[i], bk = st->beta[k];
+            double val = 0.0;
+            if (i <= k && bi > 0.0 && bk > 0.0) val = st->Tt[k * 32 + i] * 2.0 / sqrt(bi * bk);
+            T[(long long)i * ldt + k] = val;
+        }
+    }
+}
+
+int panel_generic(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb) {
+    DevBuf stb;
+    LQ_TRY(stb.alloc(c, sizeof(GPanelState)));
+    GPanelState* st = stb.as<GPanelState>();
+    const int ctas = std::max(1, std::min(c->sm_count * 2, (mp + 255) / 256));
+    const int rpc = (mp + ctas - 1) / ctas;
+    gpanel_clear_kernel<<<1, 64, 0, c->stream>>>(st, 1);
+    LQ_COUNT_LAUNCH(c);
+    for (int j = 0; j < nb; ++j) {
+        gpanel_dots_kernel<<<ctas, 256, 0, c->stream>>>(A, lda, mp, nb, j, st, rpc);
+        gpanel_update_kernel<<<ctas, 256, 0, c->stream>>>(A, lda, mp, nb, j, st, rpc);
+        gpanel_clear_kernel<<<1, 64, 0, c->stream>>>(st, 0);
+        c->launches += 3;
+    }
+    gpanel_store_kernel<<<std::min(ctas, 64), 256, 0, c->stream>>>(A, lda, V, ldv, T, ldt, mp, nb, st);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+// ------------------------------------------------------------------ cluster panel launch
+int detect_max_cluster(Ctx* c) {
+    static int cached[64] = {};
+    if (cached[c->device]) return cached[c->device];
+    auto kern = panel_cluster_kernel<4, 16>;
+    int best = 1;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int cs : {16, 8, 4, 2}) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(PANEL_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e == cudaSuccess && n >= 1) {
+            best = cs;
+            break;
+        }
+        cudaGetLastError();
+    }
+    if (const char* env = getenv("LINALG_B200_MAX_CLUSTER")) best = std::max(1, std::min(best, atoi(env)));
+    cached[c->device] = best;
+    c->max_cluster = best;
+    return best;
+}
+
+int panel_factor(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb) {
+    using Cfg = PanelCfg<4, 16>;
+    const int maxcs = detect_max_cluster(c);
+    int cs = 1;
+    while (cs * Cfg::ROWS_PER_CTA < mp && cs < maxcs) cs *= 2;
+    if (cs * Cfg::ROWS_PER_CTA < mp || nb > Cfg::NBMAX) return panel_generic(c, A, lda, V, ldv, T, ldt, mp, nb);
+    auto kern = panel_cluster_kernel<4, 16>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, A, lda, V, ldv, T, ldt, mp, nb));
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+inline int grid_for(Ctx* c, long long total) {
+    return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8));
+}
+
+// apply the block reflector  C <- (I - V op(T) V^T) C   to C (mk x nc, ldc); V (mk x kb, ldv); T (kb x kb, ldt)
+// trans_t = true -> T^T (factorisation order H_kb ... H_1), false -> T (Q formation order H_1 ... H_kb)
+int apply_block_reflector(Ctx* c, const double* V, int ldv, const double* T, int ldt, bool trans_t, int mk, int kb,
+                          double* Cm, int ldc, int nc, double* W, double* W2) {
+    if (nc <= 0 || kb <= 0 || mk <= 0) return LQ_OK;
+    LQ_TRY(gemm(c, true, false, kb, nc, mk, 1.0, V, ldv, Cm, ldc, 0.0, W, nc));           // W  = V^T C
+    LQ_TRY(gemm(c, trans_t, false, kb, nc, kb, 1.0, T, ldt, W, nc, 0.0, W2, nc));          // W2 = op(T) W
+    LQ_TRY(gemm(c, false, false, mk, nc, kb, -1.0, V, ldv, W2, nc, 1.0, Cm, ldc));         // C -= V W2
+    return LQ_OK;
+}
+
+struct Factored {
+    DevBuf Tall;     // per outer block: NB_OUT x NB_OUT
+    int nblocks = 0;
+};
+
+// A (m x npad, lda) in place; V (m x npad, ldv) zero-initialised by the caller; npad % 32 == 0.
+int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
+                  int nrhs_pad, Factored* keep) {
+    const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
+    DevBuf Tin, Tloc, G, W, W2;
+    LQ_TRY(Tin.alloc(c, sizeof(double) * NB_IN * NB_IN));
+    LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
+    const int wcols = std::max(npad, nrhs_pad);
+    LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+    LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+    if (keep) {
+        LQ_TRY(keep->Tall.alloc(c, sizeof(double) * NB_OUT * NB_OUT * (size_t)nblocks));
+        keep->nblocks = nblocks;
+    } else {
+        LQ_TRY(Tloc.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
+    }
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int k0 = blk * NB_OUT;
+        const int kb = std::min(NB_OUT, npad - k0);  // multiple of 32
+        const int mk = m - k0;
+        double* Tblk = keep ? keep->Tall.as<double>() + (size_t)blk * NB_OUT * NB_OUT : Tloc.as<double>();
+        if (mk <= 0) {
+            LQ_CUDA(c, cudaMemsetAsync(Tblk, 0, sizeof(double) * NB_OUT * NB_OUT, c->stream));
+            continue;
+        }
+        const int nin = kb / NB_IN;
+        for (int ip = 0; ip < nin; ++ip) {
+            const int c0 = k0 + ip * NB_IN;
+            const int mp = m - c0;
+            if (mp <= 0) break;
+            double* Ap = A + (size_t)c0 * lda + c0;
+            double* Vp = V + (size_t)c0 * ldv + c0;
+            double* Tp = (nin == 1) ? Tblk : Tin.as<double>();
+            const int ldtp = (nin == 1) ? NB_OUT : NB_IN;
+            LQ_TRY(panel_factor(c, Ap, lda, Vp, ldv, Tp, ldtp, mp, NB_IN));
+            const int nrem = k0 + kb - (c0 + NB_IN);
+            if (nrem > 0)
+                LQ_TRY(apply_block_reflector(c, Vp, ldv, Tp, ldtp, true, mp, NB_IN, Ap + NB_IN, lda, nrem,
+                                             W.as<double>(), W2.as<double>()));
+        }
+        const double* Vb = V + (size_t)k0 * ldv + k0;
+        if (nin > 1) {
+            LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT));
+            larft_from_gram_kernel<<<1, 128, (128 * 129 + 128) * sizeof(double), c->stream>>>(G.as<double>(), NB_OUT, Tblk,
+                                                                                              NB_OUT, kb);
+            LQ_CHECK_LAUNCH(c);
+            LQ_COUNT_LAUNCH(c);
+        }
+        const int ntr = npad - (k0 + kb);
+        if (ntr > 0)
+            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, A + (size_t)k0 * lda + k0 + kb, lda, ntr,
+                                         W.as<double>(), W2.as<double>()));
+        if (B && nrhs_pad > 0)
+            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
+                                         W.as<double>(), W2.as<double>()));
+    }
+    return LQ_OK;
+}
+
+int configure_once(Ctx* c) {
+    static bool done[64] = {};
+    if (done[c->device]) return LQ_OK;
+    LQ_CUDA(c, cudaFuncSetAttribute(larft_from_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((128 * 129 + 128) * sizeof(double))));
+    done[c->device] = true;
+    return LQ_OK;
+}
+
+// back-substitution  R X = Y  for an upper-triangular R (n x n, ldr) and Y (n x k, ldy) in place; one CTA.
+__global__ void __launch_bounds__(256) backsub_kernel(const double* __restrict__ R, int ldr, double* __restrict__ Y, int ldy,
+                                                      int n, int k) {
+    // column-parallel: thread t owns right-hand side t (looped), rows solved bottom-up
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < k; col += gridDim.x * blockDim.x) {
+        for (int i = n - 1; i >= 0; --i) {
+            double acc = Y[(long long)i * ldy + col];
+            for (int cc = i + 1; cc < n; ++cc) acc = fma(-R[(long long)i * ldr + cc], Y[(long long)cc * ldy + col], acc);
+            Y[(long long)i * ldy + col] = acc / R[(long long)i * ldr + i];
+        }
+    }
+}
+
+}  // namespace
+
+int blocked_householder_factor(Ctx* c, double* A, int lda, int m, int n, double* V, int ldv, double* B, int ldb,
+                               int nrhs) {
+    LQ_TRY(configure_once(c));
+    return factor_padded(c, A, lda, m, n, n, V, ldv, B, ldb, nrhs, nullptr);
+}
+
+int blocked_householder_qr(Ctx* c, const double* A, int m, int n, double* Q, double* R) {
+    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "householder_qr needs m >= n >= 1 (got %d x %d)", m, n);
+    LQ_TRY(configure_once(c));
+    const int npad = (n + 31) / 32 * 32;
+    DevBuf Aw, Vw, Qw;
+    LQ_TRY(Aw.alloc(c, sizeof(double) * (size_t)m * npad));
+    LQ_TRY(Vw.alloc(c, sizeof(double) * (size_t)m * npad));
+    pad_copy_kernel<<<grid_for(c, (long long)m * npad), 256, 0, c->stream>>>(A, n, Aw.as<double>(), npad, m, n, npad);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    LQ_CUDA(c, cudaMemsetAsync(Vw.p, 0, sizeof(double) * (size_t)m * npad, c->stream));
+    Factored keep;
+    LQ_TRY(factor_padded(c, Aw.as<double>(), npad, m, npad, n, Vw.as<double>(), npad, nullptr, 0, 0, &keep));
+    extract_upper_kernel<<<grid_for(c, (long long)n * n), 256, 0, c->stream>>>(Aw.as<double>(), npad, R, n);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+
+    // ---- Q = H_0 H_1 ... H_{n-1} I  (thin, m x n), block reflectors applied in reverse order
+    double* Qp = Q;
+    int ldq = n;
+    if (npad != n) {
+        LQ_TRY(Qw.alloc(c, sizeof(double) * (size_t)m * npad));
+        Qp = Qw.as<double>();
+        ldq = npad;
+    }
+    // the A workspace is free now: reuse it for W / W2
+    double* W = Aw.as<double>();
+    double* W2 = W + (size_t)NB_OUT * npad;
+    const bool ws_fits = (size_t)m * npad >= 2 * (size_t)NB_OUT * npad;
+    DevBuf Wx;
+    if (!ws_fits) {
+        LQ_TRY(Wx.alloc(c, sizeof(double) * 2 * (size_t)NB_OUT * npad));
+        W = Wx.as<double>();
+        W2 = W + (size_t)NB_OUT * npad;
+    }
+    set_identity_kernel<<<grid_for(c, (long long)m * ldq), 256, 0, c->stream>>>(Qp, ldq, m, ldq);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    for (int blk = keep.nblocks - 1; blk >= 0; --blk) {
+        const int k0 = blk * NB_OUT;
+        const int kb = std::min(NB_OUT, npad - k0);
+        const int mk = m - k0;
+        if (mk <= 0) continue;
+        const double* Vb = Vw.as<double>() + (size_t)k0 * npad + k0;
+        const double* Tblk = keep.Tall.as<double>() + (size_t)blk * NB_OUT * NB_OUT;
+        // only columns >= k0 of Q are touched by this block (Q[k0:, :k0] is still zero)
+        LQ_TRY(apply_block_reflector(c, Vb, npad, Tblk, NB_OUT, false, mk, kb, Qp + (size_t)k0 * ldq + k0, ldq, ldq - k0, W, W2));
+    }
+    if (Qp != Q) {
+        unpad_copy_kernel<<<grid_for(c, (long long)m * n), 256, 0, c->stream>>>(Qp, ldq, Q, n, m, n);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+    }
+    return LQ_OK;
+}
+
+int large_lstsq_householder(Ctx* c, const double* A, const double* B, int m, int n, int nrhs, double* X) {
+    LQ_REQUIRE(c, m >= n && n >= 1 && nrhs >= 1, LQ_ERR_SHAPE, "least squares needs m >= n >= 1, nrhs >= 1");
+    LQ_TRY(configure_once(c));
+    const int npad = (n + 31) / 32 * 32;
+    const int kpad = (nrhs + 1) / 2 * 2;
+    DevBuf Aw, Vw, Bw;
+    LQ_TRY(Aw.alloc(c, sizeof(double) * (size_t)m * npad));
+    LQ_TRY(Vw.alloc(c, sizeof(double) * (size_t)m * npad));
+    LQ_TRY(Bw.alloc(c, sizeof(double) * (size_t)m * kpad));
+    pad_copy_kernel<<<grid_for(c, (long long)m * npad), 256, 0, c->stream>>>(A, n, Aw.as<double>(), npad, m, n, npad);
+    pad_copy_kernel<<<grid_for(c, (long long)m * kpad), 256, 0, c->stream>>>(B, nrhs, Bw.as<double>(), kpad, m, nrhs, kpad);
+    LQ_CHECK_LAUNCH(c);
+    c->launches += 2;
+    LQ_CUDA(c, cudaMemsetAsync(Vw.p, 0, sizeof(double) * (size_t)m * npad, c->stream));
+    LQ_TRY(factor_padded(c, Aw.as<double>(), npad, m, npad, n, Vw.as<double>(), npad, Bw.as<double>(), kpad, kpad, nullptr));
+    backsub_kernel<<<std::max(1, (nrhs + 255) / 256), 256, 0, c->stream>>>(Aw.as<double>(), npad, Bw.as<double>(), kpad, n, nrhs);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    unpad_copy_kernel<<<grid_for(c, (long long)n * nrhs), 256, 0, c->stream>>>(Bw.as<double>(), kpad, X, nrhs, n, nrhs);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+}  // namespace lq
+
+using namespace lq;
+
+extern "C" {
+
+int lq_householder_qr_dev(lq_ctx* h, const double* A, int m, int n, double* Q, double* R) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= 1 && n >= 1 && m >= n, LQ_ERR_SHAPE, "householder_qr needs m >= n >= 1 (got %d x %d)", m, n);
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    // small problems: the one-CTA shared-memory kernel (a single launch)
+    if ((size_t)m * n <= 4096) return hh_qr_batched_stream(c, c->stream, A, 1, m, n, Q, R, -1);
+    return blocked_householder_qr(c, A, m, n, Q, R);
+}
+
+int lq_householder_qr(lq_ctx* h, const double* A, int m, int n, double* Q, double* R) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= 1 && n >= 1 && m >= n, LQ_ERR_SHAPE, "householder_qr needs m >= n >= 1 (got %d x %d)", m, n);
+    LQ_REQUIRE(c, A && Q && R, LQ_ERR_ARG, "null pointer");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    const size_t mn = sizeof(double) * (size_t)m * n, nn = sizeof(double) * (size_t)n * n;
+    DevBuf dA, dQ, dR;
+    LQ_TRY(dA.alloc(c, mn));
+    LQ_TRY(dQ.alloc(c, mn));
+    LQ_TRY(dR.alloc(c, nn));
+    LQ_CUDA(c, cudaMemcpyAsync(dA.p, A, mn, cudaMemcpyHostToDevice, c->stream));
+    LQ_TRY(lq_householder_qr_dev(h, dA.as<double>(), m, n, dQ.as<double>(), dR.as<double>()));
+    LQ_CUDA(c, cudaMemcpyAsync(Q, dQ.p, mn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(R, dR.p, nn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LQ_OK;
+}
+
+}  // extern "C"

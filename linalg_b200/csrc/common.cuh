@@ -65,35 +65,40 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 }
-// 1/x for normal, finite, non-zero x: MUFU seed + Newton steps (branch free, ~1 ulp).
-__device__ __forceinline__ double rcp_nr(double x) {
+// 1/x for normal, finite, non-zero x: MUFU seed + IT Newton steps (branch free).
+template <int IT>
+__device__ __forceinline__ double rcp_nr_t(double x) {
     double y = rcp_seed(x);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
     return y;
 }
 // 1/sqrt(x) for normal positive x.
-__device__ __forceinline__ double rsqrt_nr(double x) {
+template <int IT>
+__device__ __forceinline__ double rsqrt_nr_t(double x) {
     double y = rsqrt_seed(x);
-    double hx = 0.5 * x;
+    const double hx = 0.5 * x;
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-        double e = fma(-hx * y, y, 0.5);  // 0.5 - 0.5*x*y^2
+    for (int it = 0; it < IT; ++it) {
+        const double e = fma(-hx * y, y, 0.5);  // 0.5 - 0.5*x*y^2
         y = fma(y, e, y);
     }
     return y;
 }
 // sqrt(x) (x > 0, normal) from rsqrt with one correction step; also returns 1/sqrt(x).
-__device__ __forceinline__ double sqrt_nr(double x, double& rinv) {
-    rinv = rsqrt_nr(x);
-    double s = x * rinv;
-    double res = fma(-s, s, x);
+template <int IT>
+__device__ __forceinline__ double sqrt_nr_t(double x, double& rinv) {
+    rinv = rsqrt_nr_t<IT>(x);
+    const double s = x * rinv;
+    const double res = fma(-s, s, x);
     return fma(res, 0.5 * rinv, s);
 }
+__device__ __forceinline__ double rcp_nr(double x) { return rcp_nr_t<3>(x); }
+__device__ __forceinline__ double rsqrt_nr(double x) { return rsqrt_nr_t<3>(x); }
+__device__ __forceinline__ double sqrt_nr(double x, double& rinv) { return sqrt_nr_t<3>(x, rinv); }
 
 __device__ __forceinline__ double ld_stream(const double* p) {
     double v;

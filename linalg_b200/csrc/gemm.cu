@@ -1,0 +1,358 @@
+// Row-major FP64 GEMM  C = alpha * op(A) * op(B) + beta * C  for the blocked-QR / Gram / U=AV paths.
+//
+// Fast path: 128x128x16 CTA tiles, 8 consumer warps (2 x 4, warp tile 64x32) issuing FP64
+// tensor-core MMAs (mma.sync m16n8k8.f64 -> DMMA; tcgen05 has no f64 kind on sm_100a), fed by a
+// producer warp that streams operand rows with 1-D bulk-async copies (TMA engine, UBLKCP) into a
+// 4-stage mbarrier ring.  Shared tiles are padded (pitch 20 / 132 doubles) so every fragment load
+// is bank-conflict free.  Skinny outputs use split-K with a deterministic second-pass reduction.
+// Generic path: plain 32x32 tiled kernel for shapes/alignments the fast path does not take.
+#include "../../include/linalg_b200.h"
+#include "ops.cuh"
+
+namespace lq {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int PK = 20;    // pitch of a K-major tile  [row][k]   (16 + 4 pad)
+constexpr int PM = 132;   // pitch of an M/N-major tile [k][row] (128 + 4 pad)
+constexpr int TILE_DOUBLES = 2640;  // max(128*20, 16*132) rounded up to a multiple of 16 bytes
+constexpr int GEMM_THREADS = 288;   // 8 consumer warps + 1 producer warp
+constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+
+struct GemmArgs {
+    const double* A;
+    const double* B;
+    double* C;       // output (or split-K workspace)
+    long long M;
+    int N, K;        // K already trimmed to a multiple of BK
+    int lda, ldb, ldc;
+    double alpha, beta;
+    int splits;      // gridDim.z
+    long long split_stride;  // elements between split-K slices of the workspace
+};
+
+// AT: A is stored K x M (op(A) = A^T)  -> shared tile [k][m]   ("M-major")
+// BT: B is stored N x K (op(B) = B^T)  -> shared tile [n][k]   ("K-major")
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double));
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int mvalid = (int)min((long long)BM, g.M - m0);
+    const int nvalid = min(BN, g.N - n0);
+
+    // split-K range (in k-tiles)
+    const int KT = g.K / BK;
+    const int per = (KT + g.splits - 1) / g.splits;
+    const int kt0 = blockIdx.z * per;
+    const int kt1 = min(KT, kt0 + per);
+    const int nkt = max(0, kt1 - kt0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ===================== producer =====================
+        const uint32_t bytesA = AT ? (uint32_t)(BK * mvalid * 8) : (uint32_t)(mvalid * BK * 8);
+        const uint32_t bytesB = BT ? (uint32_t)(nvalid * BK * 8) : (uint32_t)(BK * nvalid * 8);
+        for (int it = 0; it < nkt; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            double* sA = tiles + (size_t)s * 2 * TILE_DOUBLES;
+            double* sB = sA + TILE_DOUBLES;
+            const long long k0 = (long long)(kt0 + it) * BK;
+            if (lane == 0) mbar_expect_tx(&full[s], bytesA + bytesB);
+            __syncwarp();
+            if (AT) {
+                if (lane < BK) bulk_g2s(sA + lane * PM, g.A + (k0 + lane) * g.lda + m0, mvalid * 8, &full[s]);
+            } else {
+                for (int r = lane; r < mvalid; r += 32) bulk_g2s(sA + r * PK, g.A + (m0 + r) * g.lda + k0, BK * 8, &full[s]);
+            }
+            if (BT) {
+                for (int r = lane; r < nvalid; r += 32)
+                    bulk_g2s(sB + r * PK, g.B + (long long)(n0 + r) * g.ldb + k0, BK * 8, &full[s]);
+            } else {
+                if (lane >= 16) {
+                    const int kk = lane - 16;
+                    bulk_g2s(sB + kk * PM, g.B + (k0 + kk) * g.ldb + n0, nvalid * 8, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int wm = warp >> 2, wn = warp & 3;
+    const int gq = lane >> 2, tq = lane & 3;
+    double acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+
+    for (int it = 0; it < nkt; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const double* sA = tiles + (size_t)s * 2 * TILE_DOUBLES;
+        const double* sB = sA + TILE_DOUBLES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            double af[4][4], bf[4][2];
+            const int kA = ks * 8 + tq;
+#pragma unroll
+            for (int im = 0; im < 4; ++im) {
+                const int r = wm * 64 + im * 16 + gq;
+                if (AT) {
+                    af[im][0] = sA[kA * PM + r];
+                    af[im][1] = sA[kA * PM + r + 8];
+                    af[im][2] = sA[(kA + 4) * PM + r];
+                    af[im][3] = sA[(kA + 4) * PM + r + 8];
+                } else {
+                    af[im][0] = sA[r * PK + kA];
+                    af[im][1] = sA[(r + 8) * PK + kA];
+                    af[im][2] = sA[r * PK + kA + 4];
+                    af[im][3] = sA[(r + 8) * PK + kA + 4];
+                }
+            }
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+                const int c = wn * 32 + jn * 8 + gq;
+                if (BT) {
+                    bf[jn][0] = sB[c * PK + kA];
+                    bf[jn][1] = sB[c * PK + kA + 4];
+                } else {
+                    bf[jn][0] = sB[kA * PM + c];
+                    bf[jn][1] = sB[(kA + 4) * PM + c];
+                }
+            }
+#pragma unroll
+            for (int im = 0; im < 4; ++im)
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af[im], bf[jn]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ===================== epilogue =====================
+    double* Cb = g.C + (long long)blockIdx.z * g.split_stride;
+    const bool direct = (g.splits == 1);
+    const double alpha = direct ? g.alpha : 1.0;
+    const double beta = direct ? g.beta : 0.0;
+#pragma unroll
+    for (int im = 0; im < 4; ++im) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = wm * 64 + im * 16 + gq + half * 8;
+            if (r >= mvalid) continue;
+            double* crow = Cb + (m0 + r) * (long long)g.ldc + n0;
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+                const int c = wn * 32 + jn * 8 + 2 * tq;
+                double v0 = alpha * acc[im][jn][half * 2 + 0];
+                double v1 = alpha * acc[im][jn][half * 2 + 1];
+                if (c < nvalid) {
+                    if (beta != 0.0) v0 = fma(beta, crow[c], v0);
+                    crow[c] = v0;
+                }
+                if (c + 1 < nvalid) {
+                    if (beta != 0.0) v1 = fma(beta, crow[c + 1], v1);
+                    crow[c + 1] = v1;
+                }
+            }
+        }
+    }
+}
+
+// C = alpha * sum_z W[z] + beta * C
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ W, int splits, long long stride,
+                                                            long long M, int N, double alpha, double beta, double* C,
+                                                            int ldc) {
+    const long long total = M * N;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / N;
+        const int j = (int)(e - i * N);
+        double s = 0.0;
+        for (int z = 0; z < splits; ++z) s += W[z * stride + e];
+        double* cp = C + i * ldc + j;
+        double v = alpha * s;
+        if (beta != 0.0) v = fma(beta, *cp, v);
+        *cp = v;
+    }
+}
+
+// Generic tiled kernel: any transposition, shape, leading dimension, alignment.
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(256) gemm_generic_kernel(const double* __restrict__ A, const double* __restrict__ B,
+                                                           double* __restrict__ C, long long M, int N, int K, int lda,
+                                                           int ldb, int ldc, double alpha, double beta) {
+    __shared__ double sA[32][33];
+    __shared__ double sB[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const long long m0 = (long long)blockIdx.y * 32;
+    const int n0 = blockIdx.x * 32;
+    double acc[4] = {0, 0, 0, 0};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = ty + q * 8;  // tile row index
+            // sA[r][tx] = op(A)[m0 + r][k0 + tx]
+            {
+                const long long mi = m0 + (AT ? tx : r);
+                const int ki = k0 + (AT ? r : tx);
+                double v = 0.0;
+                if (mi < M && ki < K) v = AT ? A[(long long)ki * lda + mi] : A[mi * lda + ki];
+                if (AT) sA[tx][r] = v; else sA[r][tx] = v;
+            }
+            // sB[r][tx] = op(B)[k0 + r][n0 + tx]
+            {
+                const int ki = k0 + (BT ? tx : r);
+                const int ni = n0 + (BT ? r : tx);
+                double v = 0.0;
+                if (ki < K && ni < N) v = BT ? B[(long long)ni * ldb + ki] : B[(long long)ki * ldb + ni];
+                if (BT) sB[tx][r] = v; else sB[r][tx] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const double b = sB[kk][tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fma(sA[ty + q * 8][kk], b, acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long mi = m0 + ty + q * 8;
+        const int ni = n0 + tx;
+        if (mi < M && ni < N) {
+            double v = alpha * acc[q];
+            double* cp = C + mi * ldc + ni;
+            if (beta != 0.0) v = fma(beta, *cp, v);
+            *cp = v;
+        }
+    }
+}
+
+template <bool AT, bool BT>
+int launch_generic(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                   double beta, double* C, int ldc) {
+    dim3 grid((N + 31) / 32, (unsigned)((M + 31) / 32));
+    gemm_generic_kernel<AT, BT><<<grid, 256, 0, c->stream>>>(A, B, C, M, N, K, lda, ldb, ldc, alpha, beta);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+template <bool AT, bool BT>
+int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const double* A, int lda, const double* B, int ldb,
+                double beta, double* C, int ldc) {
+    auto kern = gemm_dmma_kernel<AT, BT>;
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        configured[c->device] = true;
+    }
+    const long long tm = (M + BM - 1) / BM;
+    const int tn = (N + BN - 1) / BN;
+    const int KT = Kmain / BK;
+    int splits = 1;
+    const long long tiles = tm * tn;
+    if (tiles < 2LL * c->sm_count) {
+        splits = (int)std::min<long long>((2LL * c->sm_count + tiles - 1) / tiles, std::max(1, KT / 8));
+        splits = std::max(1, std::min(splits, 64));
+    }
+    GemmArgs g;
+    g.A = A; g.B = B; g.M = M; g.N = N; g.K = Kmain; g.lda = lda; g.ldb = ldb;
+    g.alpha = alpha; g.beta = beta; g.splits = splits;
+    DevBuf ws;
+    if (splits == 1) {
+        g.C = C; g.ldc = ldc; g.split_stride = 0;
+    } else {
+        LQ_TRY(ws.alloc(c, (size_t)splits * M * N * sizeof(double)));
+        g.C = ws.as<double>(); g.ldc = N; g.split_stride = M * (long long)N;
+    }
+    dim3 grid(tn, (unsigned)tm, splits);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, c->stream>>>(g);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    if (splits > 1) {
+        const long long total = M * N;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, c->stream>>>(ws.as<double>(), splits, g.split_stride, M, N, alpha, beta, C, ldc);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+    }
+    return LQ_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, const double* A, int lda, const double* B,
+         int ldb, double beta, double* C, int ldc) {
+    if (M <= 0 || N <= 0) return LQ_OK;
+    if (K <= 0) {
+        // C = beta * C
+        if (beta == 1.0) return LQ_OK;
+        return ta ? launch_generic<true, false>(c, M, N, 0, alpha, A, lda, B, ldb, beta, C, ldc)
+                  : launch_generic<false, false>(c, M, N, 0, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
+    const int Kmain = K - K % BK;
+    bool fast = Kmain >= BK && aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (M * (long long)N >= 64 * 64);
+    if (ta) fast = fast && (M % 2 == 0);   // M-major rows copied in whole 16-byte units
+    if (!tb) fast = fast && (N % 2 == 0);
+    if (getenv("LINALG_B200_NO_FAST_GEMM")) fast = false;
+    if (!fast) {
+        if (ta && tb) return launch_generic<true, true>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (ta) return launch_generic<true, false>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (tb) return launch_generic<false, true>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        return launch_generic<false, false>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
+    int rc;
+    if (ta && tb) rc = launch_fast<true, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (ta) rc = launch_fast<true, false>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (tb) rc = launch_fast<false, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
+    else rc = launch_fast<false, false>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (rc != LQ_OK) return rc;
+    if (Kmain < K) {
+        // K remainder: C += alpha * op(A)[:, Kmain:] * op(B)[Kmain:, :]
+        const double* A2 = ta ? A + (long long)Kmain * lda : A + Kmain;
+        const double* B2 = tb ? B + Kmain : B + (long long)Kmain * ldb;
+        const int Kr = K - Kmain;
+        if (ta && tb) return launch_generic<true, true>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
+        if (ta) return launch_generic<true, false>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
+        if (tb) return launch_generic<false, true>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
+        return launch_generic<false, false>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
+    }
+    return LQ_OK;
+}
+
+}  // namespace lq
+
+using namespace lq;
+extern "C" int lq_gemm_dev(lq_ctx* h, int transa, int transb, int64_t m, int n, int k, double alpha, const double* A,
+                           int lda, const double* B, int ldb, double beta, double* C, int ldc) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return gemm(c, transa != 0, transb != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}

@@ -3,10 +3,6 @@
 #include "ops.cuh"
 namespace lq {
 #define STUB(name) set_error(c, name ": not implemented yet"); return LQ_ERR_UNSUPPORTED
-int gemm(Ctx* c, bool, bool, long long, int, int, double, const double*, int, const double*, int, double, double*, int) { STUB("gemm"); }
-int blocked_householder_qr(Ctx* c, const double*, int, int, double*, double*) { STUB("blocked_householder_qr"); }
-int blocked_householder_factor(Ctx* c, double*, int, int, int, double*, int, double*, int, int) { STUB("blocked_householder_factor"); }
-int large_lstsq_householder(Ctx* c, const double*, const double*, int, int, int, double*) { STUB("large_lstsq_householder"); }
 int large_mgs_qr(Ctx* c, const double*, int, int, int, double*, double*, int*) { STUB("large_mgs_qr"); }
 int large_lstsq_mgs(Ctx* c, const double*, const double*, int, int, int, double*, int*) { STUB("large_lstsq_mgs"); }
 bool lstsq_stream_kernel_supported(int, int, int) { return false; }
@@ -20,15 +16,12 @@ int comm_allgather(Ctx* c, const double*, double*, long long) { STUB("comm"); }
 }
 using namespace lq;
 extern "C" {
-int lq_householder_qr_dev(lq_ctx* h, const double* A, int m, int n, double* Q, double* R) { return blocked_householder_qr(as_ctx(h), A, m, n, Q, R); }
-int lq_householder_qr(lq_ctx* h, const double*, int, int, double*, double*) { Ctx* c = as_ctx(h); STUB("householder_qr"); }
 int lq_mgs_qr_dev(lq_ctx* h, const double*, int, int, int, double*, double*, int32_t*) { Ctx* c = as_ctx(h); STUB("mgs"); }
 int lq_mgs_qr(lq_ctx* h, const double*, int, int, int, double*, double*, int32_t*) { Ctx* c = as_ctx(h); STUB("mgs"); }
 int lq_svd_gram_dev(lq_ctx* h, const double*, int64_t, int, double, double*, double*, double*, int*) { Ctx* c = as_ctx(h); STUB("svd"); }
 int lq_svd_gram(lq_ctx* h, const double*, int64_t, int, double, double*, double*, double*, int*) { Ctx* c = as_ctx(h); STUB("svd"); }
 int lq_gram_dev(lq_ctx* h, const double*, int64_t, int, double*) { Ctx* c = as_ctx(h); STUB("gram"); }
 int lq_eigh_dev(lq_ctx* h, const double*, int, double*, double*) { Ctx* c = as_ctx(h); STUB("eigh"); }
-int lq_gemm_dev(lq_ctx* h, int, int, int64_t, int, int, double, const double*, int, const double*, int, double, double*, int) { Ctx* c = as_ctx(h); STUB("gemm"); }
 int lq_tsqr_dev(lq_ctx* h, const double*, int64_t, int, double*, double*) { Ctx* c = as_ctx(h); STUB("tsqr"); }
 int lq_tsqr(lq_ctx* h, const double*, int64_t, int, double*, double*) { Ctx* c = as_ctx(h); STUB("tsqr"); }
 int lq_comm_unique_id(void*) { return LQ_ERR_UNSUPPORTED; }
