@@ -90,11 +90,14 @@ int lq_lstsq_mgs_batched(lq_ctx* ctx, const double* A, const double* B, int64_t 
 
 /* ---- a5: svd via the A^T A eigen-route  (linalg/svd.py:10-82), m >= n ------------------------- */
 /* U (m, n), s (n) descending, Vt (n, n); *rank = #(s > tol).  Columns of U beyond rank are
- * left ZERO here; the shim completes them (svd.py:67-76) with lq_householder_qr. */
+ * left ZERO here; the shim completes them (svd.py:67-76) with lq_svd_complete. */
 int lq_svd_gram_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
                     int* rank_host);
 int lq_svd_gram(lq_ctx* ctx, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
                 int* rank_host);
+/* svd.py:67-76: complete U (HOST, m x n, first `rank` columns valid) with an orthonormal basis of the
+ * complement built from the caller-drawn candidates Z (HOST, m x (n - rank)); all arithmetic on device. */
+int lq_svd_complete(lq_ctx* ctx, double* U, int64_t m, int n, int rank, const double* Z);
 /* building blocks (device pointers) */
 int lq_gram_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double* G);          /* G = A^T A (n x n) */
 int lq_eigh_dev(lq_ctx* ctx, const double* G, int n, double* lambda_desc, double* V); /* Jacobi; columns of V */
@@ -117,8 +120,9 @@ int lq_svd_gram_sharded_dev(lq_ctx* ctx, const double* A_local, int64_t m_local,
                             double* s, double* Vt, int* rank_host);
 
 /* ---- roofline probes (bench.py) --------------------------------------------------------------------- */
-/* kind 0: FP64 FMA (DFMA) peak, 1: FP64 tensor (DMMA m16n8k8) peak, 2: device copy GB/s.
- * result in TFLOP/s (kinds 0,1) or GB/s (kind 2). */
+/* kind 0: FP64 FMA (DFMA) peak, 1: FP64 tensor (DMMA m16n8k8) peak, 3: both pipes mixed [TFLOP/s];
+ * 2: device copy [GB/s]; 4: dependent DFMA latency [cycles]; 10..16: accuracy of the MUFU seeds and
+ * Newton-refined rcp / rsqrt / sqrt used by the kernels [max relative error]. */
 int lq_probe(lq_ctx* ctx, int kind, double* result);
 
 #ifdef __cplusplus

@@ -277,7 +277,7 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     const long long tiles = tm * tn;
     if (tiles < 2LL * c->sm_count) {
         splits = (int)std::min<long long>((2LL * c->sm_count + tiles - 1) / tiles, std::max(1, KT / 8));
-        splits = std::max(1, std::min(splits, 64));
+        splits = std::max(1, std::min(splits, 4 * c->sm_count));
     }
     GemmArgs g;
     g.A = A; g.B = B; g.M = M; g.N = N; g.K = Kmain; g.lda = lda; g.ldb = ldb;
@@ -317,7 +317,7 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
                   : launch_generic<false, false>(c, M, N, 0, alpha, A, lda, B, ldb, beta, C, ldc);
     }
     const int Kmain = K - K % BK;
-    bool fast = Kmain >= BK && aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (M * (long long)N >= 64 * 64);
+    bool fast = Kmain >= BK && aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (M * (long long)N >= 32 * 32);
     if (ta) fast = fast && (M % 2 == 0);   // M-major rows copied in whole 16-byte units
     if (!tb) fast = fast && (N % 2 == 0);
     if (getenv("LINALG_B200_NO_FAST_GEMM")) fast = false;

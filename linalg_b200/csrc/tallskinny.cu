@@ -1,0 +1,486 @@
+// K5: tall-skinny paths -- Gram matrix, symmetric eigen-solver, economy SVD (linalg/svd.py:10-82)
+// and TSQR, with the NCCL exchange steps of the row-sharded variants.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/linalg_b200.h"
+#include "ops.cuh"
+#include "stream_qr.cuh"
+
+namespace lq {
+
+namespace {
+
+inline int grid_for(Ctx* c, long long total) {
+    return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8));
+}
+
+// ------------------------------------------------------------------ Jacobi eigen-solver
+// Two-sided cyclic Jacobi with the round-robin ("circle") parallel ordering.  One CTA owns the
+// matrix (shared memory when it fits, global memory otherwise); every round applies n/2 disjoint
+// rotations, first to the columns then to the rows.  The (c, s) pairs are logged so that the
+// eigenvectors can be accumulated afterwards by independent CTAs (one row of V each).
+__device__ __forceinline__ void rr_pair(int n_even, int round, int k, int& p, int& q) {
+    // players 0..n_even-2 on a circle, player n_even-1 fixed
+    const int mod = n_even - 1;
+    int a, b;
+    if (k == 0) {
+        a = n_even - 1;
+        b = round % mod;
+    } else {
+        a = (round + k) % mod;
+        b = (round - k + mod) % mod;
+    }
+    p = min(a, b);
+    q = max(a, b);
+}
+
+__global__ void __launch_bounds__(512) jacobi_kernel(const double* __restrict__ G, int n, double* __restrict__ Awork,
+                                                     int use_global, double2* __restrict__ rotlog, int max_sweeps,
+                                                     int* __restrict__ nrounds_out, double* __restrict__ lambda) {
+    extern __shared__ __align__(16) double sm[];
+    const int ne = (n + 1) & ~1;          // padded to even; the pad index never rotates (zero coupling)
+    const int ld = ne | 1;                // odd pitch
+    double* Am = use_global ? Awork : sm;
+    double2* cs = reinterpret_cast<double2*>(use_global ? sm : sm + (size_t)ne * ld + (ne & 1 ? 1 : 0) + 1);
+    // align cs to 16 bytes
+    cs = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(cs) + 15) & ~(uintptr_t)15);
+    __shared__ int s_rot;
+    __shared__ double s_scale;
+    __shared__ int2 pq[1024];  // pairs of the current round (n <= 2048)
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int half = ne / 2;
+
+    for (int e = tid; e < ne * ne; e += nt) {
+        const int i = e / ne, j = e - i * ne;
+        Am[(size_t)i * ld + j] = (i < n && j < n) ? G[(size_t)i * n + j] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double g = 0.0;
+        for (int i = 0; i < n; ++i) g = fmax(g, fabs(Am[(size_t)i * ld + i]));
+        s_scale = g;
+    }
+    __syncthreads();
+    const double floor_abs = 4.9303806576313238e-32 * s_scale;  // eps^2 * max|diag|
+
+    int rounds = 0;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int rd = 0; rd < ne - 1; ++rd, ++rounds) {
+            // rotation parameters of this round
+            for (int kk = tid; kk < half; kk += nt) {
+                int p, q;
+                rr_pair(ne, rd, kk, p, q);
+                pq[kk] = make_int2(p, q);
+                const double app = Am[(size_t)p * ld + p], aqq = Am[(size_t)q * ld + q], apq = Am[(size_t)p * ld + q];
+                double cc = 1.0, ss = 0.0;
+                if (fabs(apq) > floor_abs && fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq))) {
+                    const double tau = (aqq - app) / (2.0 * apq);
+                    const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    cc = 1.0 / sqrt(1.0 + t * t);
+                    ss = t * cc;
+                    atomicAdd(&s_rot, 1);
+                }
+                cs[kk] = make_double2(cc, ss);
+                rotlog[(size_t)rounds * half + kk] = make_double2(cc, ss);
+            }
+            __syncthreads();
+            // columns: A[:, p], A[:, q]
+            for (int e = tid; e < half * ne; e += nt) {
+                const int k = e / ne, i = e - k * ne;
+                const int p = pq[k].x, q = pq[k].y;
+                const double2 r2 = cs[k];
+                const double ap = Am[(size_t)i * ld + p], aq = Am[(size_t)i * ld + q];
+                Am[(size_t)i * ld + p] = r2.x * ap - r2.y * aq;
+                Am[(size_t)i * ld + q] = r2.y * ap + r2.x * aq;
+            }
+            __syncthreads();
+            // rows: A[p, :], A[q, :]
+            for (int e = tid; e < half * ne; e += nt) {
+                const int k = e / ne, j = e - k * ne;
+                const int p = pq[k].x, q = pq[k].y;
+                const double2 r2 = cs[k];
+                const double ap = Am[(size_t)p * ld + j], aq = Am[(size_t)q * ld + j];
+                Am[(size_t)p * ld + j] = r2.x * ap - r2.y * aq;
+                Am[(size_t)q * ld + j] = r2.y * ap + r2.x * aq;
+            }
+            __syncthreads();
+        }
+        const int nrot = s_rot;
+        __syncthreads();
+        if (nrot == 0) break;
+    }
+    if (tid == 0) *nrounds_out = rounds;
+    for (int i = tid; i < n; i += nt) lambda[i] = Am[(size_t)i * ld + i];
+}
+
+// V = J_1 J_2 ... (rows of the identity transformed independently): CTA b owns row b of V.
+__global__ void __launch_bounds__(256) jacobi_apply_kernel(const double2* __restrict__ rotlog, const int* __restrict__ nrounds,
+                                                           int n, double* __restrict__ V) {
+    extern __shared__ double row[];
+    const int ne = (n + 1) & ~1, half = ne / 2;
+    const int b = blockIdx.x;
+    for (int j = threadIdx.x; j < ne; j += blockDim.x) row[j] = (j == b) ? 1.0 : 0.0;
+    __syncthreads();
+    const int R = *nrounds;
+    for (int rd = 0; rd < R; ++rd) {
+        const int rr = rd % (ne - 1);
+        for (int k = threadIdx.x; k < half; k += blockDim.x) {
+            int p, q;
+            rr_pair(ne, rr, k, p, q);
+            const double2 r2 = rotlog[(size_t)rd * half + k];
+            const double vp = row[p], vq = row[q];
+            row[p] = r2.x * vp - r2.y * vq;
+            row[q] = r2.y * vp + r2.x * vq;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) V[(size_t)b * n + j] = row[j];
+}
+
+// sort eigenvalues descending (rank by counting), permute the columns of V accordingly
+__global__ void __launch_bounds__(256) eig_sort_kernel(const double* __restrict__ lam_in, const double* __restrict__ Vin, int n,
+                                                       double* __restrict__ lam_out, double* __restrict__ Vout) {
+    extern __shared__ int rank_of[];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double li = lam_in[i];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) {
+            const double lj = lam_in[j];
+            rk += (lj > li) || (lj == li && j < i);
+        }
+        rank_of[i] = rk;
+        lam_out[rk] = li;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int r = e / n, cidx = e - r * n;
+        Vout[(size_t)r * n + rank_of[cidx]] = Vin[e];
+    }
+}
+
+// s = sqrt(max(lambda, 0)); M2 = V diag(1/s for s > tol else 0); Vt = V^T; rank = #(s > tol)
+__global__ void __launch_bounds__(256) svd_post_kernel(const double* __restrict__ lam, const double* __restrict__ V, int n,
+                                                       double tol, double* __restrict__ s, double* __restrict__ M2,
+                                                       double* __restrict__ Vt, int* __restrict__ rank) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double sj = sqrt(fmax(lam[j], 0.0));
+        s[j] = sj;
+        if (sj > tol) atomicAdd(&cnt, 1);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e - i * n;
+        const double sj = sqrt(fmax(lam[j], 0.0));
+        const double v = V[e];
+        M2[e] = (sj > tol) ? v / sj : 0.0;
+        Vt[(size_t)j * n + i] = v;
+    }
+    if (threadIdx.x == 0) *rank = cnt;
+}
+
+// ------------------------------------------------------------------ small triangular helpers (single CTA)
+// Rinv = R^{-1} for an upper-triangular R (n x n, row-major); column-parallel back substitution.
+__global__ void __launch_bounds__(256) triu_inverse_kernel(const double* __restrict__ R, int n, double* __restrict__ Rinv) {
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n; col += gridDim.x * blockDim.x) {
+        for (int i = n - 1; i >= 0; --i) {
+            double acc = (i == col) ? 1.0 : 0.0;
+            if (i > col) {
+                Rinv[(size_t)i * n + col] = 0.0;
+                continue;
+            }
+            for (int k = i + 1; k <= col; ++k) acc = fma(-R[(size_t)i * n + k], Rinv[(size_t)k * n + col], acc);
+            Rinv[(size_t)i * n + col] = acc / R[(size_t)i * n + i];
+        }
+    }
+}
+// make diag(R) > 0: R <- S R, and return S (n) so that Q <- Q S
+__global__ void __launch_bounds__(256) sign_fix_R_kernel(double* __restrict__ R, int n, double* __restrict__ sgn) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double sg = (R[(size_t)i * n + i] < 0.0) ? -1.0 : 1.0;
+        sgn[i] = sg;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n;
+        R[e] *= sgn[i];
+    }
+}
+__global__ void __launch_bounds__(256) scale_cols_kernel(double* __restrict__ M, int n, const double* __restrict__ sgn) {
+    // M <- M * diag(sgn)   (n x n)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) M[e] *= sgn[e % n];
+}
+
+int eigh_configure(Ctx* c) {
+    static bool done[64] = {};
+    if (done[c->device]) return LQ_OK;
+    LQ_CUDA(c, cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    LQ_CUDA(c, cudaFuncSetAttribute(tsqr_leaf_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    done[c->device] = true;
+    return LQ_OK;
+}
+
+// R factor (n x n upper) of A (m x n, lda) by a tree of streaming Householder reductions
+int tsqr_rfactor(Ctx* c, const double* A, int lda, long long m, int n, double* R /* n x n */) {
+    using Cfg = StreamCfg<4, 16, 8>;
+    const size_t smem = Cfg::smem_doubles(n) * sizeof(double);
+    const double* cur = A;
+    int cur_ld = lda;
+    long long cur_m = m;
+    DevBuf bufs[2];
+    int flip = 0;
+    for (int level = 0; level < 8; ++level) {
+        // leaves of >= 4 blocks each, at most 2 CTAs per SM worth of leaves
+        long long min_rows = (long long)Cfg::BLOCK_ROWS * 8;
+        long long ctas = std::max<long long>(1, std::min<long long>((long long)c->sm_count, cur_m / min_rows));
+        if (level > 0) ctas = std::max<long long>(1, std::min<long long>(ctas, cur_m / ((long long)n * 8)));
+        long long rpc = (cur_m + ctas - 1) / ctas;
+        rpc = (rpc + Cfg::BLOCK_ROWS - 1) / Cfg::BLOCK_ROWS * Cfg::BLOCK_ROWS;
+        ctas = (cur_m + rpc - 1) / rpc;
+        double* out;
+        if (ctas == 1) {
+            out = R;
+        } else {
+            LQ_TRY(bufs[flip].alloc(c, sizeof(double) * (size_t)ctas * n * n));
+            out = bufs[flip].as<double>();
+        }
+        tsqr_leaf_kernel<16, 8><<<(unsigned)ctas, 256, smem, c->stream>>>(cur, cur_ld, cur_m, n, rpc, out);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+        if (ctas == 1) return LQ_OK;
+        cur = out;
+        cur_ld = n;
+        cur_m = ctas * (long long)n;
+        flip ^= 1;
+    }
+    set_error(c, "tsqr_rfactor: reduction tree did not terminate");
+    return LQ_ERR_ARG;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ public (internal) ops
+int gram(Ctx* c, const double* A, long long m, int n, double* G) {
+    return gemm(c, true, false, n, n, (int)m, 1.0, A, n, A, n, 0.0, G, n);
+}
+
+int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) {
+    LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_UNSUPPORTED, "eigen-solver supports n <= 2048 (got %d)", n);
+    LQ_TRY(eigh_configure(c));
+    const int ne = (n + 1) & ~1, ld = ne | 1, half = ne / 2;
+    const int max_sweeps = 40;
+    const size_t need = ((size_t)ne * ld + 4) * sizeof(double) + (size_t)half * sizeof(double2) + 64;
+    const int use_global = need + 9216 > (size_t)c->max_smem;  // 9 KB of static shared memory in the kernel
+    DevBuf Aw, rot, nr, lam, Vraw;
+    LQ_TRY(Aw.alloc(c, use_global ? sizeof(double) * (size_t)ne * ld : 16));
+    LQ_TRY(rot.alloc(c, sizeof(double2) * (size_t)max_sweeps * (ne - 1 > 0 ? ne - 1 : 1) * (half > 0 ? half : 1)));
+    LQ_TRY(nr.alloc(c, 16));
+    LQ_TRY(lam.alloc(c, sizeof(double) * n));
+    LQ_TRY(Vraw.alloc(c, sizeof(double) * (size_t)n * n));
+    const size_t smem = use_global ? (size_t)half * sizeof(double2) + 64 : need;
+    jacobi_kernel<<<1, 512, smem, c->stream>>>(G, n, Aw.as<double>(), use_global, rot.as<double2>(), max_sweeps,
+                                               nr.as<int>(), lam.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    jacobi_apply_kernel<<<n, 128, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, Vraw.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
+    LQ_CHECK_LAUNCH(c);
+    c->launches += 3;
+    return LQ_OK;
+}
+
+int svd_gram_local(Ctx* c, const double* A, long long m, int n, double tol, double* U, double* s, double* Vt,
+                   int* rank_host, bool sharded) {
+    LQ_REQUIRE(c, m >= 1 && n >= 1, LQ_ERR_SHAPE, "svd: bad shape %lld x %d", m, n);
+    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "svd: more than 2^31 rows per device not supported");
+    DevBuf G, lam, V, M2, rk;
+    LQ_TRY(G.alloc(c, sizeof(double) * (size_t)n * n));
+    LQ_TRY(lam.alloc(c, sizeof(double) * n));
+    LQ_TRY(V.alloc(c, sizeof(double) * (size_t)n * n));
+    LQ_TRY(M2.alloc(c, sizeof(double) * (size_t)n * n));
+    LQ_TRY(rk.alloc(c, 16));
+    LQ_TRY(gram(c, A, m, n, G.as<double>()));                                  // svd.py:42
+    if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
+    LQ_TRY(eigh_jacobi(c, G.as<double>(), n, lam.as<double>(), V.as<double>())); // svd.py:46-51
+    svd_post_kernel<<<1, 256, 0, c->stream>>>(lam.as<double>(), V.as<double>(), n, tol, s, M2.as<double>(), Vt, rk.as<int>());
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, M2.as<double>(), n, 0.0, U, n));  // svd.py:61-64
+    if (rank_host) {
+        LQ_CUDA(c, cudaMemcpyAsync(rank_host, rk.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return LQ_OK;
+}
+
+// TSQR: R by a Householder reduction tree (leaves stream their rows, R factors are combined),
+// Q = A R^{-1} followed by one TSQR refinement pass (restores orthogonality to O(eps) whenever
+// cond(A) * eps << 1), signs normalised so that diag(R) > 0 -- the MGS convention (qr.py:39-42).
+int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
+    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "tsqr needs m >= n >= 1 (got %lld x %d)", m, n);
+    LQ_REQUIRE(c, n <= 128, LQ_ERR_UNSUPPORTED, "tsqr supports n <= 128 (got %d); use householder_qr", n);
+    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "tsqr: more than 2^31 rows per device not supported");
+    LQ_TRY(eigh_configure(c));
+    DevBuf R1, R2, Rinv, Rall, sgn, Q1;
+    const size_t nn = sizeof(double) * (size_t)n * n;
+    LQ_TRY(R1.alloc(c, nn));
+    LQ_TRY(R2.alloc(c, nn));
+    LQ_TRY(Rinv.alloc(c, nn));
+    LQ_TRY(sgn.alloc(c, sizeof(double) * n));
+    LQ_TRY(Q1.alloc(c, sizeof(double) * (size_t)m * n));
+    if (sharded && c->nranks > 1) LQ_TRY(Rall.alloc(c, nn * c->nranks));
+
+    auto reduce_R = [&](const double* X, double* Rout) -> int {
+        LQ_TRY(tsqr_rfactor(c, X, n, m, n, Rout));
+        if (sharded && c->nranks > 1) {
+            // exchange step: all-gather the local R factors, every rank reduces the same stack
+            LQ_TRY(comm_allgather(c, Rout, Rall.as<double>(), (long long)n * n));
+            LQ_TRY(tsqr_rfactor(c, Rall.as<double>(), n, (long long)c->nranks * n, n, Rout));
+        }
+        return LQ_OK;
+    };
+    // pass 1
+    LQ_TRY(reduce_R(A, R1.as<double>()));
+    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R1.as<double>(), n, Rinv.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, Rinv.as<double>(), n, 0.0, Q1.as<double>(), n));
+    // pass 2 (refinement)
+    LQ_TRY(reduce_R(Q1.as<double>(), R2.as<double>()));
+    sign_fix_R_kernel<<<1, 256, 0, c->stream>>>(R2.as<double>(), n, sgn.as<double>());   // R2 <- S R2 (temporarily, S folded below)
+    LQ_CHECK_LAUNCH(c);
+    // we want R = S' (R2 R1) with diag > 0.  Compute R = R2 R1 first with the unsigned R2:
+    //   sign_fix made diag(R2) > 0; R1's diagonal sign decides the final flip.
+    LQ_TRY(gemm(c, false, false, n, n, n, 1.0, R2.as<double>(), n, R1.as<double>(), n, 0.0, R, n));
+    // Q = Q1 (S R2)^{-1} ... then flip so that diag(R) > 0
+    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R2.as<double>(), n, Rinv.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    sign_fix_R_kernel<<<1, 256, 0, c->stream>>>(R, n, sgn.as<double>());                  // R <- S2 R
+    scale_cols_kernel<<<grid_for(c, (long long)n * n), 256, 0, c->stream>>>(Rinv.as<double>(), n, sgn.as<double>());  // Rinv <- Rinv S2
+    LQ_CHECK_LAUNCH(c);
+    c->launches += 5;
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, Q1.as<double>(), n, Rinv.as<double>(), n, 0.0, Q, n));
+    return LQ_OK;
+}
+
+}  // namespace lq
+
+using namespace lq;
+
+extern "C" {
+
+int lq_gram_dev(lq_ctx* h, const double* A, int64_t m, int n, double* G) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= 1 && n >= 1 && m < (1LL << 31), LQ_ERR_SHAPE, "gram: bad shape");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return gram(c, A, m, n, G);
+}
+int lq_eigh_dev(lq_ctx* h, const double* G, int n, double* lambda_desc, double* V) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_SHAPE, "eigh: n must be in [1, 2048] (got %d)", n);
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return eigh_jacobi(c, G, n, lambda_desc, V);
+}
+int lq_svd_gram_dev(lq_ctx* h, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
+                    int* rank_host) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= n, LQ_ERR_SHAPE, "svd_gram needs m >= n (transpose on the host side, svd.py:37-39)");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return svd_gram_local(c, A, m, n, tol, U, s, Vt, rank_host, false);
+}
+int lq_svd_gram_sharded_dev(lq_ctx* h, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
+                            int* rank_host) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return svd_gram_local(c, A, m, n, tol, U, s, Vt, rank_host, true);
+}
+int lq_svd_gram(lq_ctx* h, const double* A, int64_t m, int n, double tol, double* U, double* s, double* Vt,
+                int* rank_host) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "svd_gram needs m >= n >= 1");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    const size_t mn = sizeof(double) * (size_t)m * n, nn = sizeof(double) * (size_t)n * n;
+    DevBuf dA, dU, ds, dVt;
+    LQ_TRY(dA.alloc(c, mn));
+    LQ_TRY(dU.alloc(c, mn));
+    LQ_TRY(ds.alloc(c, sizeof(double) * n));
+    LQ_TRY(dVt.alloc(c, nn));
+    LQ_CUDA(c, cudaMemcpyAsync(dA.p, A, mn, cudaMemcpyHostToDevice, c->stream));
+    LQ_TRY(svd_gram_local(c, dA.as<double>(), m, n, tol, dU.as<double>(), ds.as<double>(), dVt.as<double>(), rank_host, false));
+    LQ_CUDA(c, cudaMemcpyAsync(U, dU.p, mn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(s, ds.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(Vt, dVt.p, nn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LQ_OK;
+}
+// linalg/svd.py:67-76 on the device: orthonormal completion of U (host, m x n, first `rank` columns
+// valid) from the candidate directions Z (host, m x (n - rank), drawn by the caller).
+int lq_svd_complete(lq_ctx* h, double* U, int64_t m, int n, int rank, const double* Z) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    const int k = n - rank;
+    LQ_REQUIRE(c, m >= n && rank >= 0 && k >= 1 && U && Z, LQ_ERR_SHAPE, "svd_complete: bad arguments");
+    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "svd_complete: too many rows");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    DevBuf dU, dZ, dQ, dR, dW;
+    LQ_TRY(dU.alloc(c, sizeof(double) * (size_t)m * n));
+    LQ_TRY(dZ.alloc(c, sizeof(double) * (size_t)m * k));
+    LQ_TRY(dQ.alloc(c, sizeof(double) * (size_t)m * k));
+    LQ_TRY(dR.alloc(c, sizeof(double) * (size_t)k * k));
+    LQ_TRY(dW.alloc(c, sizeof(double) * (size_t)n * k));
+    LQ_CUDA(c, cudaMemcpyAsync(dU.p, U, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(dZ.p, Z, sizeof(double) * (size_t)m * k, cudaMemcpyHostToDevice, c->stream));
+    LQ_TRY(lq_householder_qr_dev(h, dZ.as<double>(), (int)m, k, dQ.as<double>(), dR.as<double>()));          // svd.py:69
+    if (rank > 0) {
+        // Q -= U_r (U_r^T Q)                                                                                // svd.py:71-72
+        LQ_TRY(gemm(c, true, false, rank, k, (int)m, 1.0, dU.as<double>(), n, dQ.as<double>(), k, 0.0, dW.as<double>(), k));
+        LQ_TRY(gemm(c, false, false, m, k, rank, -1.0, dU.as<double>(), n, dW.as<double>(), k, 1.0, dQ.as<double>(), k));
+    }
+    LQ_TRY(lq_householder_qr_dev(h, dQ.as<double>(), (int)m, k, dZ.as<double>(), dR.as<double>()));          // svd.py:74
+    // U[:, rank:] = Z
+    LQ_CUDA(c, cudaMemcpy2DAsync(U + rank, sizeof(double) * n, dZ.p, sizeof(double) * k, sizeof(double) * k, (size_t)m,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LQ_OK;
+}
+
+int lq_tsqr_dev(lq_ctx* h, const double* A, int64_t m, int n, double* Q, double* R) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return tsqr_local(c, A, m, n, Q, R, false);
+}
+int lq_tsqr_sharded_dev(lq_ctx* h, const double* A, int64_t m, int n, double* Q, double* R) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return tsqr_local(c, A, m, n, Q, R, true);
+}
+int lq_tsqr(lq_ctx* h, const double* A, int64_t m, int n, double* Q, double* R) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "tsqr needs m >= n >= 1");
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    const size_t mn = sizeof(double) * (size_t)m * n, nn = sizeof(double) * (size_t)n * n;
+    DevBuf dA, dQ, dR;
+    LQ_TRY(dA.alloc(c, mn));
+    LQ_TRY(dQ.alloc(c, mn));
+    LQ_TRY(dR.alloc(c, nn));
+    LQ_CUDA(c, cudaMemcpyAsync(dA.p, A, mn, cudaMemcpyHostToDevice, c->stream));
+    LQ_TRY(tsqr_local(c, dA.as<double>(), m, n, dQ.as<double>(), dR.as<double>(), false));
+    LQ_CUDA(c, cudaMemcpyAsync(Q, dQ.p, mn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(R, dR.p, nn, cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LQ_OK;
+}
+
+}  // extern "C"
