@@ -1,0 +1,391 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-generated golden
+fixtures.  Bars (BASELINE.json north_star): Q, R elementwise relative 1e-10 under the reference's
+sign convention; ||A - QR|| / ||A|| <= 1e-12; max|Q^T Q - I| <= 1e-12; least-squares solutions and
+singular values relative 1e-10."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import linalg_b200 as lb
+from conftest import golden_cases
+from oracle import linalg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+RESID = 1e-12
+ORTH = 1e-12
+
+
+def check_qr(A, Q, R, Qo, Ro, rel=REL, mgs=False):
+    assert Q.shape == Qo.shape and R.shape == Ro.shape
+    assert orc.rel_max_err(Q, Qo) <= rel, ("Q", orc.rel_max_err(Q, Qo))
+    assert orc.rel_max_err(R, Ro) <= rel, ("R", orc.rel_max_err(R, Ro))
+    assert np.all(np.tril(R, -1) == 0.0)
+    if not mgs:  # one-sweep MGS loses orthogonality like the reference does; compared elementwise only
+        assert orc.orth_error(Q) <= ORTH
+    assert orc.qr_residual(A, Q, R) <= RESID
+
+
+# ------------------------------------------------------------------ a1 Householder, golden fixtures
+@pytest.mark.parametrize("name", golden_cases("hh"))
+def test_householder_golden(ctx, golden, name):
+    A = golden[f"hh/{name}/A"]
+    Q, R = lb.householder_qr(A, ctx=ctx)
+    Qo, Ro = golden[f"hh/{name}/Q"], golden[f"hh/{name}/R"]
+    assert Q.shape == Qo.shape and R.shape == Ro.shape
+    assert orc.rel_max_err(Q, Qo) <= REL and orc.rel_max_err(R, Ro) <= REL
+    assert np.all(np.tril(R, -1) == 0.0)
+    if name != "all_zero":
+        assert orc.qr_residual(A, Q, R) <= RESID
+    assert orc.orth_error(Q) <= ORTH
+
+
+@pytest.mark.parametrize("name", golden_cases("mgs"))
+def test_mgs_golden(ctx, golden, name):
+    A = golden[f"mgs/{name}/A"]
+    Q, R = lb.qr(A, ctx=ctx)
+    check_qr(A, Q, R, golden[f"mgs/{name}/Q"], golden[f"mgs/{name}/R"], mgs=True)
+    assert np.all(np.diag(R) > 0)
+
+
+@pytest.mark.parametrize("name", golden_cases("mgs_reorth"))
+def test_mgs_reorth_golden(ctx, golden, name):
+    A = golden[f"mgs_reorth/{name}/A"]
+    Q, R = lb.qr(A, reorth=True, ctx=ctx)
+    # the reference returns the SECOND sweep's R (~I), so Q @ R != A by design (qr.py:46-47)
+    assert orc.rel_max_err(Q, golden[f"mgs_reorth/{name}/Q"]) <= REL
+    assert np.max(np.abs(R - golden[f"mgs_reorth/{name}/R"])) <= 1e-10
+    assert orc.orth_error(Q) <= ORTH
+
+
+def test_batched32_golden(ctx, golden):
+    A = golden["batched32/A"]
+    Q, R = lb.householder_qr_batched(A, ctx=ctx)
+    assert orc.rel_max_err(Q, golden["batched32/Q_hh"]) <= REL and orc.rel_max_err(R, golden["batched32/R_hh"]) <= REL
+    Q, R = lb.qr_batched(A, ctx=ctx)
+    assert orc.rel_max_err(Q, golden["batched32/Q_mgs"]) <= REL and orc.rel_max_err(R, golden["batched32/R_mgs"]) <= REL
+
+
+# ------------------------------------------------------------------ cfg2: batched 32x32
+@pytest.mark.parametrize("batch", [1, 3, 5, 33, 1000])
+def test_batched32_ragged_batches(ctx, batch):
+    A = np.random.default_rng(100 + batch).standard_normal((batch, 32, 32))
+    Q, R = lb.householder_qr_batched(A, ctx=ctx)
+    Qo, Ro = orc.householder_qr_batched(A)
+    for i in range(0, batch, max(1, batch // 16)):
+        check_qr(A[i], Q[i], R[i], Qo[i], Ro[i])
+    assert orc.rel_max_err(Q, Qo) <= REL and orc.rel_max_err(R, Ro) <= REL
+    Q, R = lb.qr_batched(A, ctx=ctx)
+    Qo, Ro = orc.mgs_qr_batched(A)
+    assert orc.rel_max_err(Q, Qo) <= REL and orc.rel_max_err(R, Ro) <= REL
+    Q, R = lb.qr_batched(A, reorth=True, ctx=ctx)
+    Qo, Ro = orc.mgs_qr_batched(A, reorth=True)
+    assert orc.rel_max_err(Q, Qo) <= REL and np.max(np.abs(R - Ro)) <= 1e-10
+
+
+def test_batched32_empty_batch(ctx):
+    Q, R = lb.householder_qr_batched(np.zeros((0, 32, 32)), ctx=ctx)
+    assert Q.shape == (0, 32, 32) and R.shape == (0, 32, 32)
+
+
+def test_batched32_special_matrices(ctx):
+    """Skip branch (||x|| < 1e-12, qr.py:79-80), negative/zero pivots, identity, tiny and huge scales."""
+    rng = np.random.default_rng(77)
+    A = rng.standard_normal((12, 32, 32))
+    A[0] = 0.0
+    A[1] = np.eye(32)
+    A[2] = -np.eye(32)
+    A[3][:, 5] = 0.0
+    A[4] = np.triu(A[4])
+    A[5] *= 1e-6
+    A[6] *= 1e6
+    A[7][:, 0] = 0.0
+    A[7][0, 0] = 0.0
+    A[8] = np.tril(A[8])
+    A[9][10:, :] = 0.0  # rank 10: later columns hit the skip branch after elimination (tiny norms)
+    Q, R = lb.householder_qr_batched(A, ctx=ctx)
+    Qo, Ro = orc.householder_qr_batched(A)
+    for i in range(12):
+        if i == 9:
+            # rank-deficient: reflectors of the numerically-zero tail are rounding noise in the
+            # reference too; only the invariants are meaningful
+            assert orc.qr_residual(A[i], Q[i], R[i]) <= RESID and orc.orth_error(Q[i]) <= ORTH
+            continue
+        assert orc.rel_max_err(Q[i], Qo[i]) <= REL, i
+        assert orc.rel_max_err(R[i], Ro[i]) <= REL, i
+    assert np.all(np.tril(R, -1) == 0.0)
+
+
+def test_batched32_device_resident_full_size(ctx):
+    """2^20 matrices resident in HBM (BASELINE cfg2) through the _dev entry points: parity on a
+    strided subsample, invariants on another, determinism across replicas of the same input."""
+    uniq, reps = 1 << 14, 64
+    batch = uniq * reps
+    A = np.random.default_rng(2).standard_normal((uniq, 32, 32))
+    per = A.nbytes
+    dA, dQ, dR = ctx.alloc(per * reps), ctx.alloc(per * reps), ctx.alloc(per * reps)
+    ctx.call("lq_memcpy_h2d", dA.ptr, A.ctypes.data, per)
+    for r in range(1, reps):
+        ctx.call("lq_memcpy_d2d", dA.ptr + r * per, dA.ptr, per)
+    for which in ("hh", "mgs"):
+        if which == "hh":
+            ctx.call("lq_householder_qr_batched_dev", dA.ptr, batch, 32, 32, dQ.ptr, dR.ptr, 0)
+        else:
+            dI = ctx.alloc(4 * batch)
+            ctx.call("lq_mgs_qr_batched_dev", dA.ptr, batch, 32, 32, 0, dQ.ptr, dR.ptr, dI.ptr)
+        ctx.sync()
+        Q0, R0 = np.empty_like(A), np.empty_like(A)
+        ctx.call("lq_memcpy_d2h", Q0.ctypes.data, dQ.ptr, per)
+        ctx.call("lq_memcpy_d2h", R0.ctypes.data, dR.ptr, per)
+        ctx.sync()
+        Ql, Rl = np.empty_like(A), np.empty_like(A)
+        ctx.call("lq_memcpy_d2h", Ql.ctypes.data, dQ.ptr + (reps - 1) * per, per)
+        ctx.call("lq_memcpy_d2h", Rl.ctypes.data, dR.ptr + (reps - 1) * per, per)
+        ctx.sync()
+        assert np.array_equal(Q0, Ql) and np.array_equal(R0, Rl)  # same input -> same bits, any replica
+        sub = np.arange(0, uniq, 64)
+        fn = orc.householder_qr_batched if which == "hh" else orc.mgs_qr_batched
+        Qo, Ro = fn(A[sub])
+        assert orc.rel_max_err(Q0[sub], Qo) <= REL and orc.rel_max_err(R0[sub], Ro) <= REL
+        resid = np.linalg.norm(A - Q0 @ R0, axis=(1, 2)) / np.linalg.norm(A, axis=(1, 2))
+        assert resid.max() <= RESID
+        if which == "hh":
+            G = np.swapaxes(Q0, 1, 2) @ Q0 - np.eye(32)
+            assert np.abs(G).max() <= ORTH
+            assert np.all(np.tril(R0, -1) == 0.0)
+        else:
+            info = np.empty(batch, dtype=np.int32)
+            ctx.call("lq_memcpy_d2h", info.ctypes.data, dI.ptr, info.nbytes)
+            ctx.sync()
+            assert not info.any()
+
+
+def test_mgs_dependent_columns_raise(ctx):
+    A = np.random.default_rng(5).standard_normal((32, 32))
+    A[:, 7] = A[:, 3]
+    with pytest.raises(ValueError, match="linearly dependent"):
+        lb.qr(A, ctx=ctx)
+    B = np.random.default_rng(6).standard_normal((4, 32, 32))
+    B[2][:, 9] = 2.0 * B[2][:, 1]
+    with pytest.raises(ValueError, match="linearly dependent"):
+        lb.qr_batched(B, ctx=ctx)
+    with pytest.raises(ValueError, match="linearly dependent"):
+        lb.qr(np.ones((6, 3)), ctx=ctx)
+    with pytest.raises(ValueError):
+        lb.qr(np.random.default_rng(1).standard_normal((3, 5)), ctx=ctx)  # m < n: always dependent
+
+
+# ------------------------------------------------------------------ generic shapes (one CTA per matrix)
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 2), (7, 3), (33, 32), (64, 64), (100, 10), (128, 100), (31, 31), (200, 50)])
+def test_small_generic_shapes(ctx, m, n):
+    A = np.random.default_rng(1000 + m * n).standard_normal((3, m, n))
+    Q, R = lb.householder_qr_batched(A, ctx=ctx)
+    Qo, Ro = orc.householder_qr_batched(A)
+    for i in range(3):
+        check_qr(A[i], Q[i], R[i], Qo[i], Ro[i])
+    Q, R = lb.qr_batched(A, ctx=ctx)
+    Qo, Ro = orc.mgs_qr_batched(A)
+    assert orc.rel_max_err(Q, Qo) <= REL and orc.rel_max_err(R, Ro) <= REL
+
+
+# ------------------------------------------------------------------ cfg1 / cfg4: single matrix, blocked compact-WY
+@pytest.mark.parametrize("m,n", [(256, 256), (300, 300), (512, 256), (700, 130), (1000, 1000), (1024, 1024), (2000, 40)])
+def test_blocked_householder_vs_oracle(ctx, m, n):
+    A = np.random.default_rng(m + n).standard_normal((m, n))
+    Q, R = lb.householder_qr(A, ctx=ctx)
+    Qo, Ro = orc.householder_qr(A)
+    check_qr(A, Q, R, np.ascontiguousarray(Qo), Ro)
+
+
+def test_blocked_householder_zero_columns_and_integers(ctx):
+    A = np.random.default_rng(9).integers(-9, 10, (384, 200)).astype(np.float64)
+    A[:, 17] = 0.0
+    A[:, 130] = 0.0
+    Q, R = lb.householder_qr(A, ctx=ctx)
+    Qo, Ro = orc.householder_qr(A)
+    check_qr(A, Q, R, np.ascontiguousarray(Qo), Ro)
+    assert not np.shares_memory(Q, A)
+
+
+def test_blocked_2048_lapack_crosscheck(ctx):
+    """At 2048^2 the reference needs ~46 s; cross-check against LAPACK with the documented sign
+    difference (last row of R / last column of Q negated) plus the invariants."""
+    n = 2048
+    A = np.random.default_rng(5).standard_normal((n, n))
+    Q, R = lb.householder_qr(A, ctx=ctx)
+    Ql, Rl = np.linalg.qr(A)
+    Rl[-1] *= -1.0
+    Ql[:, -1] *= -1.0
+    assert orc.rel_max_err(R, Rl) <= REL and orc.rel_max_err(Q, Ql) <= 1e-9
+    assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
+    assert np.all(np.tril(R, -1) == 0.0)
+
+
+def test_blocked_8192_full_size_properties(ctx):
+    """BASELINE cfg4 at full size, device resident.  O(n^3) checks are unaffordable on the host, so
+    the invariants are probed with random vectors: A x = Q (R x), Q^T (Q x) = x, plus the sign rule
+    R[j,j] = -copysign(||x||, x0) checked on column 0 and exact zeros below the diagonal."""
+    n = 8192
+    A = np.random.default_rng(5).standard_normal((n, n))
+    dA, dQ, dR = ctx.upload(A), ctx.alloc(A.nbytes), ctx.alloc(A.nbytes)
+    ctx.call("lq_householder_qr_dev", dA.ptr, n, n, dQ.ptr, dR.ptr)
+    Q = ctx.download(dQ, (n, n))
+    R = ctx.download(dR, (n, n))
+    X = np.random.default_rng(6).standard_normal((n, 4))
+    AX = A @ X
+    assert np.linalg.norm(AX - Q @ (R @ X)) / np.linalg.norm(AX) <= 1e-12
+    assert np.linalg.norm(Q.T @ (Q @ X) - X) / np.linalg.norm(X) <= 1e-12
+    assert np.linalg.norm(Q @ (Q.T @ X) - X) / np.linalg.norm(X) <= 1e-12
+    assert np.all(np.tril(R, -1) == 0.0)
+    assert abs(R[0, 0] + np.copysign(np.linalg.norm(A[:, 0]), A[0, 0])) <= 1e-10 * abs(R[0, 0])
+    assert np.allclose(np.abs(np.diag(R))[:8], np.abs(np.diag(np.linalg.qr(A[:, :8])[1])), rtol=1e-10)
+
+
+def test_gemm_building_block(ctx):
+    rng = np.random.default_rng(3)
+    for ta, tb, M, N, K in [(0, 0, 200, 136, 48), (1, 0, 128, 256, 4096), (0, 0, 4096, 128, 128), (1, 1, 33, 17, 9),
+                            (0, 1, 130, 70, 35), (1, 0, 32, 96, 2048)]:
+        Ah = rng.standard_normal((K, M) if ta else (M, K))
+        Bh = rng.standard_normal((N, K) if tb else (K, N))
+        Ch = rng.standard_normal((M, N))
+        dA, dB, dC = ctx.upload(Ah), ctx.upload(Bh), ctx.upload(Ch)
+        ctx.call("lq_gemm_dev", ta, tb, M, N, K, C.c_double(0.5), dA.ptr, Ah.shape[1], dB.ptr, Bh.shape[1],
+                 C.c_double(2.0), dC.ptr, N)
+        got = ctx.download(dC, (M, N))
+        want = 0.5 * (Ah.T if ta else Ah) @ (Bh.T if tb else Bh) + 2.0 * Ch
+        assert orc.rel_max_err(got, want) <= 1e-13, (ta, tb, M, N, K)
+
+
+# ------------------------------------------------------------------ a3 / a4: least squares
+@pytest.mark.parametrize("name", golden_cases("ls"))
+def test_least_squares_golden(ctx, golden, name):
+    A = golden[f"ls/{name}/A"]
+    if name == "cfg3":
+        B = golden["ls/cfg3/B"]
+        X = lb.least_squares_householder_qr_batched(A, B, ctx=ctx)
+        assert X.shape == (2, 64, 16) and orc.rel_max_err(X.reshape(2, -1), golden["ls/cfg3/X_hh"].reshape(2, -1)) <= REL
+        X = lb.least_squares_qr_batched(A, B, ctx=ctx)
+        assert X.shape == (2, 64 * 16) and orc.rel_max_err(X, golden["ls/cfg3/X_mgs"]) <= REL
+        return
+    b = golden[f"ls/{name}/b"]
+    xh = lb.least_squares_householder_qr(A, b, ctx=ctx)
+    xm = lb.least_squares_qr(A, b, ctx=ctx)
+    assert xh.shape == golden[f"ls/{name}/x_hh"].shape and xm.shape == golden[f"ls/{name}/x_mgs"].shape
+    if name.startswith("upper50"):
+        # tests/test_qr.py:23-47: the bar is the infinity-norm residual against lstsq, rtol 1e-8
+        res_np = np.linalg.norm(A @ np.linalg.lstsq(A, b, rcond=None)[0] - b, np.inf)
+        bound = max(res_np * (1 + 1e-8), 1e-9 * np.linalg.norm(b, np.inf))
+        assert np.linalg.norm(A @ xh - b, np.inf) <= bound
+        assert np.linalg.norm(A @ xm - b, np.inf) <= bound
+    else:
+        assert orc.rel_max_err(xh, golden[f"ls/{name}/x_hh"]) <= REL
+        assert orc.rel_max_err(xm, golden[f"ls/{name}/x_mgs"]) <= REL
+
+
+def test_least_squares_cfg3_batch(ctx):
+    """cfg3 shape class (256 x 64, 16 right-hand sides), 192 systems against the oracle loop."""
+    A = np.random.default_rng(3).standard_normal((192, 256, 64))
+    B = np.random.default_rng(4).standard_normal((192, 256, 16))
+    X = lb.least_squares_householder_qr_batched(A, B, ctx=ctx)
+    assert orc.rel_max_err(X, orc.lstsq_householder_batched(A, B)) <= REL
+    Xm = lb.least_squares_qr_batched(A, B, ctx=ctx)
+    assert orc.rel_max_err(Xm, orc.lstsq_mgs_batched(A, B)) <= REL
+    # normal equations hold: A^T (A x - b) = 0
+    r = A @ X - B
+    g = np.swapaxes(A, 1, 2) @ r
+    assert np.abs(g).max() <= 1e-10
+
+
+@pytest.mark.parametrize("m,n,k", [(50, 50, 1), (40, 12, 3), (100, 30, 7), (300, 64, 16), (64, 64, 32), (600, 200, 5), (33, 7, 40)])
+def test_least_squares_shapes(ctx, m, n, k):
+    A = np.random.default_rng(m).standard_normal((m, n))
+    B = np.random.default_rng(k).standard_normal((m, k))
+    x = lb.least_squares_householder_qr(A, B, ctx=ctx)
+    assert x.shape == (n, k) and orc.rel_max_err(x, orc.lstsq_householder(A, B)) <= 1e-9
+    xm = lb.least_squares_qr(A, B, ctx=ctx)
+    assert xm.shape == (n * k,) and orc.rel_max_err(xm, orc.lstsq_mgs(A, B)) <= 1e-9
+    xv = lb.least_squares_householder_qr(A, B[:, 0], ctx=ctx)
+    assert xv.shape == (n,) and orc.rel_max_err(xv, x[:, 0]) <= 1e-12
+
+
+# ------------------------------------------------------------------ a5: svd via A^T A
+def _align(Vt, Vt_ref):
+    return np.sign(np.sum(Vt * Vt_ref, axis=1))
+
+
+@pytest.mark.parametrize("name", golden_cases("svd"))
+def test_svd_golden(ctx, golden, name):
+    A = golden[f"svd/{name}/A"]
+    np.random.seed(999)
+    U, s, Vt = lb.svd(A, ctx=ctx)
+    s_ref, Vt_ref = golden[f"svd/{name}/s"], golden[f"svd/{name}/Vt"]
+    assert s.shape == s_ref.shape and Vt.shape == Vt_ref.shape
+    np.testing.assert_allclose(s, s_ref, rtol=1e-10, atol=1e-12)  # tests/test_svd.py:52
+    r = int(np.sum(s_ref > 1e-8))
+    sg = _align(Vt[:r], Vt_ref[:r])
+    assert orc.rel_max_err(Vt[:r] * sg[:, None], Vt_ref[:r]) <= 1e-8  # tests/test_svd.py:56-57
+    k = min(A.shape)
+    assert np.linalg.norm((U[:, :k] * s[:k]) @ Vt[:k] - A) < 1e-10  # tests/test_svd.py:24
+    if A.shape[0] >= A.shape[1]:
+        assert np.abs(U.T @ U - np.eye(U.shape[1])).max() <= 1e-10  # also the completed columns
+    assert np.abs(Vt @ Vt.T - np.eye(Vt.shape[0])).max() <= 1e-10
+    if f"svd/{name}/U" in golden:
+        U_ref = golden[f"svd/{name}/U"]
+        assert U.shape == U_ref.shape
+        if A.shape[0] >= A.shape[1]:
+            assert orc.rel_max_err(U[:, :r] * sg[None, :r], U_ref[:, :r]) <= 1e-8
+
+
+def test_svd_tall_skinny(ctx):
+    A = np.random.default_rng(6).standard_normal((1 << 17, 128))
+    U, s, Vt = lb.svd(A, ctx=ctx)
+    _, so, Vto = orc.svd_gram(A)
+    assert np.max(np.abs(s - so) / so) <= REL
+    assert np.linalg.norm((U * s) @ Vt - A) / np.linalg.norm(A) <= 1e-12
+    assert np.abs(U.T @ U - np.eye(128)).max() <= 1e-10
+    assert np.all(np.diff(s) <= 0)
+
+
+def test_eigh_building_block(ctx):
+    for n in (1, 2, 5, 64, 127, 128, 200):
+        M = np.random.default_rng(n).standard_normal((n + 5, n))
+        G = M.T @ M
+        dG, dl, dV = ctx.upload(G), ctx.alloc(8 * n), ctx.alloc(8 * n * n)
+        ctx.call("lq_eigh_dev", dG.ptr, n, dl.ptr, dV.ptr)
+        lam = ctx.download(dl, (n,))
+        V = ctx.download(dV, (n, n))
+        ref = np.linalg.eigvalsh(G)[::-1]
+        assert np.max(np.abs(lam - ref)) <= 1e-12 * ref[0]
+        assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-12
+        assert np.abs(G @ V - V * lam).max() <= 1e-11 * ref[0]
+
+
+# ------------------------------------------------------------------ a7: TSQR
+def test_tsqr_matches_mgs_convention(ctx, golden):
+    A = golden["tsqr/mgs_1024x64/A"]
+    Q, R = lb.tsqr(A, ctx=ctx)
+    assert orc.rel_max_err(R, golden["tsqr/mgs_1024x64/R"]) <= REL
+    assert np.all(np.diag(R) > 0) and np.all(np.tril(R, -1) == 0.0)
+    assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
+    Qm, Rm = orc.mgs_qr(A)
+    assert orc.rel_max_err(Q, Qm) <= 1e-9
+
+
+@pytest.mark.parametrize("m,n", [(128, 128), (1000, 17), (5000, 100), (1 << 16, 128), (300001, 64)])
+def test_tsqr_shapes(ctx, m, n):
+    A = np.random.default_rng(m % 1000 + n).standard_normal((m, n))
+    Q, R = lb.tsqr(A, ctx=ctx)
+    Qo, Ro = orc.tsqr_reference(A)
+    assert orc.rel_max_err(R, Ro) <= REL and orc.rel_max_err(Q, Qo) <= 1e-9
+    assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
+
+
+def test_no_cpu_fallback_loaded(ctx):
+    """The numbers above came from the in-tree CUDA library: it is the loaded object and it counted launches."""
+    from linalg_b200 import _native
+
+    assert ctx.launches() > 0
+    maps = open("/proc/self/maps").read()
+    assert _native.LIB_PATH in maps
