@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(256)
             for (int i = tid; i < m; i += nt) part = fma(qj[i], qj[i], part);
             const double nrm = sqrt(block_sum(part, red));
             if (nrm < kEps && bad == 0) bad = j + 1;  // qr.py:40-41
-            const double rinv = 1.0 / nrm;
             __syncthreads();
-            for (int i = tid; i < m; i += nt) qj[i] *= rinv;
+            // true division, like the reference's  v / R[j, j]  (qr.py:42): on (near-)triangular inputs the
+            // quotient is exactly +-1 and the zeros below stay exact, which tests/test_qr.py:23-47 relies on
+            for (int i = tid; i < m; i += nt) qj[i] = qj[i] / nrm;
             if (tid == 0) Rs[(size_t)j * nc + j] = nrm;
             __syncthreads();
             for (int c = j + 1 + warp; c < nc; c += nw) {

@@ -46,8 +46,7 @@ __global__ void __launch_bounds__(256) mgs_norm_kernel(double* __restrict__ At, 
         R[(size_t)j * n + j] = nrm;
         if (nrm < kEps && info && *info == 0) *info = j + 1;  // qr.py:40-41
     }
-    const double rinv = 1.0 / nrm;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] *= rinv;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = v[i] / nrm;  // true division, qr.py:42
 }
 // columns c > j: r = q_j . a_c ; a_c -= r q_j ; R[j][c] = r      (one CTA per column)
 __global__ void __launch_bounds__(256) mgs_update_kernel(double* __restrict__ At, int m, int n, int j, double* __restrict__ R) {

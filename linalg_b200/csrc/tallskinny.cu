@@ -219,8 +219,13 @@ __global__ void __launch_bounds__(256) scale_cols_kernel(double* __restrict__ M,
 int eigh_configure(Ctx* c) {
     static bool done[64] = {};
     if (done[c->device]) return LQ_OK;
-    LQ_CUDA(c, cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    LQ_CUDA(c, cudaFuncSetAttribute(tsqr_leaf_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    cudaFuncAttributes fa{};
+    LQ_CUDA(c, cudaFuncGetAttributes(&fa, jacobi_kernel));
+    LQ_CUDA(c, cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    c->max_smem - (int)fa.sharedSizeBytes));
+    LQ_CUDA(c, cudaFuncGetAttributes(&fa, tsqr_leaf_kernel<16, 8>));
+    LQ_CUDA(c, cudaFuncSetAttribute(tsqr_leaf_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    c->max_smem - (int)fa.sharedSizeBytes));
     done[c->device] = true;
     return LQ_OK;
 }
