@@ -48,12 +48,12 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
     if (m == 32 && n == 32 && variant >= 0) {
         switch (variant) {
             case 0:
+            case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // default: 2 Newton steps
             case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
             case 2: return launch_hh32<1, 2, 4, false, 2>(c, st, A, batch, Q, R);
             case 3: return launch_hh32<2, 2, 4, false, 4>(c, st, A, batch, Q, R);
             case 4: return launch_hh32<2, 4, 2, false, 5>(c, st, A, batch, Q, R);
-            case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);
             case 7: return launch_hh32<2, 4, 1, true, 8>(c, st, A, batch, Q, R);
             case 8: return launch_hh32<4, 4, 4, true, 4>(c, st, A, batch, Q, R);
             case 9: return launch_hh32<4, 4, 4, true, 3>(c, st, A, batch, Q, R);

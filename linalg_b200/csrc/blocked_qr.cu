@@ -90,6 +90,53 @@ __global__ void __launch_bounds__(128) larft_from_gram_kernel(const double* __re
     }
 }
 
+// Merge the 32 x 32 panel factors on the diagonal of T (kb x kb, kb = 32 * nblk <= 128) into the factor of
+// the whole outer block, using the Gram matrix G = V^T V:  for column block b = 1 .. nblk-1
+//     T[0:R, b] = -T[0:R, 0:R] * G[0:R, b] * T[b, b],   R = 32 b
+// (the block form of LAPACK dlarft; V1 := the first R reflectors).  One CTA, everything in shared memory.
+__global__ void __launch_bounds__(256) merge_t_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T, int ldt,
+                                                      int kb) {
+    extern __shared__ double sh[];
+    double* Ts = sh;               // [128][129]
+    double* Xs = Ts + 128 * 129;   // [96][33]
+    double* Ys = Xs + 96 * 33;     // [96][33]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nblk = kb / 32;
+    for (int e = tid; e < kb * kb; e += nt) {
+        const int i = e / kb, k = e - i * kb;
+        const bool diag_block = (i / 32 == k / 32);
+        Ts[i * 129 + k] = (diag_block && k >= i) ? T[(long long)i * ldt + k] : 0.0;
+    }
+    __syncthreads();
+    for (int b = 1; b < nblk; ++b) {
+        const int R = 32 * b, c0 = 32 * b;
+        for (int e = tid; e < R * 32; e += nt) {
+            const int i = e >> 5, cc = e & 31;
+            Xs[i * 33 + cc] = G[(long long)i * ldg + c0 + cc];
+        }
+        __syncthreads();
+        for (int e = tid; e < R * 32; e += nt) {
+            const int i = e >> 5, cc = e & 31;
+            double acc = 0.0;
+            for (int k = i; k < R; ++k) acc = fma(Ts[i * 129 + k], Xs[k * 33 + cc], acc);
+            Ys[i * 33 + cc] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < R * 32; e += nt) {
+            const int i = e >> 5, cc = e & 31;
+            double acc = 0.0;
+            for (int k = 0; k <= cc; ++k) acc = fma(Ys[i * 33 + k], Ts[(c0 + k) * 129 + c0 + cc], acc);
+            Ts[i * 129 + c0 + cc] = -acc;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < kb * kb; e += nt) {
+        const int i = e / kb, k = e - i * kb;
+        T[(long long)i * ldt + k] = Ts[i * 129 + k];
+    }
+}
+constexpr size_t MERGE_T_SMEM = (128 * 129 + 2 * 96 * 33) * sizeof(double);
+
 // ------------------------------------------------------------------ generic (any height) panel, BLAS-2, multi-launch
 // Used only when the panel does not fit the cluster kernel (mp > 16 * 512 rows).  Column j:
 //   k1: per-CTA partial  x^T P[:, c]  for all c -> atomicAdd into acc[0:nb]; pivot row copied to acc[nb:2nb]
@@ -291,8 +338,7 @@ struct Factored {
 int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
-    DevBuf Tin, Tloc, G, W, W2;
-    LQ_TRY(Tin.alloc(c, sizeof(double) * NB_IN * NB_IN));
+    DevBuf Tloc, G, W, W2;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
@@ -313,14 +359,15 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             continue;
         }
         const int nin = kb / NB_IN;
+        LQ_CUDA(c, cudaMemsetAsync(Tblk, 0, sizeof(double) * NB_OUT * NB_OUT, c->stream));
         for (int ip = 0; ip < nin; ++ip) {
             const int c0 = k0 + ip * NB_IN;
             const int mp = m - c0;
             if (mp <= 0) break;
             double* Ap = A + (size_t)c0 * lda + c0;
             double* Vp = V + (size_t)c0 * ldv + c0;
-            double* Tp = (nin == 1) ? Tblk : Tin.as<double>();
-            const int ldtp = (nin == 1) ? NB_OUT : NB_IN;
+            double* Tp = Tblk + (size_t)ip * NB_IN * NB_OUT + ip * NB_IN;  // diagonal block of the outer T
+            const int ldtp = NB_OUT;
             LQ_TRY(panel_factor(c, Ap, lda, Vp, ldv, Tp, ldtp, mp, NB_IN));
             const int nrem = k0 + kb - (c0 + NB_IN);
             if (nrem > 0)
@@ -330,8 +377,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         const double* Vb = V + (size_t)k0 * ldv + k0;
         if (nin > 1) {
             LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT));
-            larft_from_gram_kernel<<<1, 128, (128 * 129 + 128) * sizeof(double), c->stream>>>(G.as<double>(), NB_OUT, Tblk,
-                                                                                              NB_OUT, kb);
+            merge_t_kernel<<<1, 256, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
             LQ_CHECK_LAUNCH(c);
             LQ_COUNT_LAUNCH(c);
         }
@@ -351,6 +397,7 @@ int configure_once(Ctx* c) {
     if (done[c->device]) return LQ_OK;
     LQ_CUDA(c, cudaFuncSetAttribute(larft_from_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)((128 * 129 + 128) * sizeof(double))));
+    LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
     done[c->device] = true;
     return LQ_OK;
 }

@@ -6,6 +6,8 @@
 // 4-stage mbarrier ring.  Shared tiles are padded (pitch 20 / 132 doubles) so every fragment load
 // is bank-conflict free.  Skinny outputs use split-K with a deterministic second-pass reduction.
 // Generic path: plain 32x32 tiled kernel for shapes/alignments the fast path does not take.
+#include <cuda.h>  // CUtensorMap types only; the encoder is resolved through cudaGetDriverEntryPoint (no -lcuda)
+
 #include "../../include/linalg_b200.h"
 #include "ops.cuh"
 
@@ -14,11 +16,53 @@ namespace lq {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-constexpr int PK = 20;    // pitch of a K-major tile  [row][k]   (16 + 4 pad)
-constexpr int PM = 132;   // pitch of an M/N-major tile [k][row] (128 + 4 pad)
-constexpr int TILE_DOUBLES = 2640;  // max(128*20, 16*132) rounded up to a multiple of 16 bytes
+constexpr int PM = 132;   // pitch of an M/N-major tile [k][row] (128 + 4 pad), filled by 16 one-row bulk copies
+// A K-major tile [row][k] is 128 rows x 16 doubles = 128 rows x 128 B: ONE 2-D TMA box with the 128-byte
+// swizzle (16-byte chunk c of row r lands at chunk c ^ (r & 7)), which makes the DMMA fragment loads
+// bank-conflict free without padding.  (128 separate 128-byte bulk copies per stage halved the NN rate.)
+constexpr int TILE_BYTES = 17408;   // 17 KiB >= max(128*128, 16*132*8), multiple of 1024 (swizzle alignment)
+constexpr int TILE_DOUBLES = TILE_BYTES / 8;
 constexpr int GEMM_THREADS = 288;   // 8 consumer warps + 1 producer warp
-constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * TILE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// tensor map of a row-major (rows x cols, ld) float64 matrix, box = 128 rows x 16 columns, 128-byte swizzle
+int make_kmajor_map(Ctx* c, CUtensorMap* map, const double* base, long long rows, long long cols, long long ld) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    LQ_REQUIRE(c, enc != nullptr, LQ_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LQ_REQUIRE(c, r == CUDA_SUCCESS, LQ_ERR_CUDA_BASE + 1, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return LQ_OK;
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// element (r, k) of a swizzled K-major tile (r & 7 must be passed as r7)
+__device__ __forceinline__ int sw_idx(int r, int r7, int k) { return r * BK + ((((k >> 1) ^ r7) << 1) | (k & 1)); }
 
 struct GemmArgs {
     const double* A;
@@ -35,10 +79,13 @@ struct GemmArgs {
 // AT: A is stored K x M (op(A) = A^T)  -> shared tile [k][m]   ("M-major")
 // BT: B is stored N x K (op(B) = B^T)  -> shared tile [n][k]   ("K-major")
 template <bool AT, bool BT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmArgs g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_dmma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw =
+        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * 2 * TILE_BYTES);
     uint64_t* empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,8 +112,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmAr
 
     if (warp == 8) {
         // ===================== producer =====================
-        const uint32_t bytesA = AT ? (uint32_t)(BK * mvalid * 8) : (uint32_t)(mvalid * BK * 8);
-        const uint32_t bytesB = BT ? (uint32_t)(nvalid * BK * 8) : (uint32_t)(BK * nvalid * 8);
+        // a TMA box always delivers its full size (out-of-range rows arrive as zeros)
+        const uint32_t bytesA = AT ? (uint32_t)(BK * mvalid * 8) : (uint32_t)(BM * BK * 8);
+        const uint32_t bytesB = BT ? (uint32_t)(BN * BK * 8) : (uint32_t)(BK * nvalid * 8);
         for (int it = 0; it < nkt; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -79,11 +127,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmAr
             if (AT) {
                 if (lane < BK) bulk_g2s(sA + lane * PM, g.A + (k0 + lane) * g.lda + m0, mvalid * 8, &full[s]);
             } else {
-                for (int r = lane; r < mvalid; r += 32) bulk_g2s(sA + r * PK, g.A + (m0 + r) * g.lda + k0, BK * 8, &full[s]);
+                if (lane == 0) tma_load_2d(sA, &mapA, (int)k0, (int)m0, &full[s]);
             }
             if (BT) {
-                for (int r = lane; r < nvalid; r += 32)
-                    bulk_g2s(sB + r * PK, g.B + (long long)(n0 + r) * g.ldb + k0, BK * 8, &full[s]);
+                if (lane == 1) tma_load_2d(sB, &mapB, (int)k0, n0, &full[s]);
             } else {
                 if (lane >= 16) {
                     const int kk = lane - 16;
@@ -124,18 +171,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmAr
                     af[im][2] = sA[(kA + 4) * PM + r];
                     af[im][3] = sA[(kA + 4) * PM + r + 8];
                 } else {
-                    af[im][0] = sA[r * PK + kA];
-                    af[im][1] = sA[(r + 8) * PK + kA];
-                    af[im][2] = sA[r * PK + kA + 4];
-                    af[im][3] = sA[(r + 8) * PK + kA + 4];
+                    af[im][0] = sA[sw_idx(r, gq, kA)];
+                    af[im][1] = sA[sw_idx(r + 8, gq, kA)];
+                    af[im][2] = sA[sw_idx(r, gq, kA + 4)];
+                    af[im][3] = sA[sw_idx(r + 8, gq, kA + 4)];
                 }
             }
 #pragma unroll
             for (int jn = 0; jn < 4; ++jn) {
                 const int c = wn * 32 + jn * 8 + gq;
                 if (BT) {
-                    bf[jn][0] = sB[c * PK + kA];
-                    bf[jn][1] = sB[c * PK + kA + 4];
+                    bf[jn][0] = sB[sw_idx(c, gq, kA)];
+                    bf[jn][1] = sB[sw_idx(c, gq, kA + 4)];
                 } else {
                     bf[jn][0] = sB[kA * PM + c];
                     bf[jn][1] = sB[(kA + 4) * PM + c];
@@ -151,12 +198,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmAr
     }
 
     // ===================== epilogue =====================
+    // Two-phase per 16-row band: all the C loads of the band are issued before any dependent FMA / store,
+    // so a thread pays one global round trip per band instead of one per element (the rank-128 update
+    // C -= V W spends as long in this epilogue as in its 8 k-tiles otherwise).
     double* Cb = g.C + (long long)blockIdx.z * g.split_stride;
     const bool direct = (g.splits == 1);
     const double alpha = direct ? g.alpha : 1.0;
     const double beta = direct ? g.beta : 0.0;
+    const bool vec2 = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
 #pragma unroll
     for (int im = 0; im < 4; ++im) {
+        double cold[2][4][2];
+        if (beta != 0.0) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = wm * 64 + im * 16 + gq + half * 8;
+                const double* crow = Cb + (m0 + r) * (long long)g.ldc + n0;
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + 2 * tq;
+                    cold[half][jn][0] = 0.0;
+                    cold[half][jn][1] = 0.0;
+                    if (r < mvalid) {
+                        if (vec2 && c + 1 < nvalid) {
+                            const double2 t2 = *reinterpret_cast<const double2*>(crow + c);
+                            cold[half][jn][0] = t2.x;
+                            cold[half][jn][1] = t2.y;
+                        } else {
+                            if (c < nvalid) cold[half][jn][0] = crow[c];
+                            if (c + 1 < nvalid) cold[half][jn][1] = crow[c + 1];
+                        }
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = wm * 64 + im * 16 + gq + half * 8;
@@ -167,13 +242,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(const GemmAr
                 const int c = wn * 32 + jn * 8 + 2 * tq;
                 double v0 = alpha * acc[im][jn][half * 2 + 0];
                 double v1 = alpha * acc[im][jn][half * 2 + 1];
-                if (c < nvalid) {
-                    if (beta != 0.0) v0 = fma(beta, crow[c], v0);
-                    crow[c] = v0;
+                if (beta != 0.0) {
+                    v0 = fma(beta, cold[half][jn][0], v0);
+                    v1 = fma(beta, cold[half][jn][1], v1);
                 }
-                if (c + 1 < nvalid) {
-                    if (beta != 0.0) v1 = fma(beta, crow[c + 1], v1);
-                    crow[c + 1] = v1;
+                if (vec2 && c + 1 < nvalid) {
+                    *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);
+                } else {
+                    if (c < nvalid) crow[c] = v0;
+                    if (c + 1 < nvalid) crow[c + 1] = v1;
                 }
             }
         }
@@ -275,9 +352,22 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     const int KT = Kmain / BK;
     int splits = 1;
     const long long tiles = tm * tn;
-    if (tiles < 2LL * c->sm_count) {
-        splits = (int)std::min<long long>((2LL * c->sm_count + tiles - 1) / tiles, std::max(1, KT / 8));
-        splits = std::max(1, std::min(splits, 4 * c->sm_count));
+    if (tiles < 2LL * c->sm_count && KT >= 16) {
+        // split K so that tiles * splits fills whole waves of SMs (one CTA per SM): pick the split count in
+        // [1, KT/8] with the best wave efficiency, preferring fewer splits (less workspace traffic) on ties
+        const int max_splits = (int)std::min<long long>(std::max(1, KT / 8), (4LL * c->sm_count + tiles - 1) / tiles);
+        double best_eff = 0.0;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const long long ctas = tiles * sp;
+            const long long waves = (ctas + c->sm_count - 1) / c->sm_count;
+            // cost model: waves * (k-tiles per CTA + fixed per-CTA overhead of ~6 k-tiles)
+            const double per = (double)((KT + sp - 1) / sp) + 6.0;
+            const double eff = 1.0 / (waves * per);
+            if (eff > best_eff * 1.02) {
+                best_eff = eff;
+                splits = sp;
+            }
+        }
     }
     GemmArgs g;
     g.A = A; g.B = B; g.M = M; g.N = N; g.K = Kmain; g.lda = lda; g.ldb = ldb;
@@ -289,8 +379,13 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
         LQ_TRY(ws.alloc(c, (size_t)splits * M * N * sizeof(double)));
         g.C = ws.as<double>(); g.ldc = N; g.split_stride = M * (long long)N;
     }
+    CUtensorMap mapA, mapB;
+    memset(&mapA, 0, sizeof(mapA));
+    memset(&mapB, 0, sizeof(mapB));
+    if (!AT) LQ_TRY(make_kmajor_map(c, &mapA, A, M, Kmain, lda));   // A stored M x K
+    if (BT) LQ_TRY(make_kmajor_map(c, &mapB, B, N, Kmain, ldb));    // B stored N x K
     dim3 grid(tn, (unsigned)tm, splits);
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, c->stream>>>(g);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, c->stream>>>(g, mapA, mapB);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
     if (splits > 1) {
