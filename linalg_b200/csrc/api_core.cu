@@ -204,7 +204,11 @@ int lq_create(int device, lq_ctx** out) {
     }
     c->sm_count = c->prop.multiProcessorCount;
     c->max_smem = (int)c->prop.sharedMemPerBlockOptin;
-    LQ_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the context stream carries the latency-bound chains (panel factorisations); the side lanes carry bulk
+    // work that overlaps with them, so the main stream gets the higher scheduling priority
+    int prio_lo = 0, prio_hi = 0;
+    LQ_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    LQ_CUDA(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 2; ++i) LQ_CUDA(c, cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) LQ_CUDA(c, cudaEventCreate(&c->ev[i]));
     // keep freed scratch cached in the stream-ordered pool

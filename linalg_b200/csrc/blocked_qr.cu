@@ -334,32 +334,74 @@ struct Factored {
     int nblocks = 0;
 };
 
+// run a scope of library calls on another stream of the context (the host side is single threaded per context)
+struct StreamScope {
+    Ctx* c;
+    cudaStream_t saved;
+    StreamScope(Ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamScope() { c->stream = saved; }
+};
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+    int make(Ctx* c, cudaEvent_t* out) {
+        LQ_CUDA(c, cudaEventCreateWithFlags(out, cudaEventDisableTiming));
+        ev.push_back(*out);
+        return LQ_OK;
+    }
+};
+
 // A (m x npad, lda) in place; V (m x npad, ldv) zero-initialised by the caller; npad % 32 == 0.
+//
+// Look-ahead schedule over two streams.  The panel chain of outer block b (four cluster-panel kernels, the
+// narrow updates between them, Gram + T merge) is latency bound and uses 16 SMs; the trailing update with
+// block b is throughput bound.  So after block b is factored, the context stream (high priority) applies it
+// to the columns of block b+1 only and goes straight on to factor block b+1, while the side stream applies
+// block b to all the remaining columns (and to the right-hand sides).  Dependencies:
+//     side:  rest(b)  after panel(b)                    [event ev_panel[b]]   and after rest(b-1) [stream order]
+//     main:  next(b)  after rest(b-1)                   [event ev_rest[b-1]]  (block b+1's columns were in rest(b-1))
 int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
-    DevBuf Tloc, G, W, W2;
+    cudaStream_t s_main = c->stream, s_side = c->lane[0];
+    const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
+    DevBuf Tloc, G, W, W2, Ws, W2s;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+    if (lookahead) {
+        LQ_TRY(Ws.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+        LQ_TRY(W2s.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+    }
+    double* Tall;
     if (keep) {
         LQ_TRY(keep->Tall.alloc(c, sizeof(double) * NB_OUT * NB_OUT * (size_t)nblocks));
         keep->nblocks = nblocks;
+        Tall = keep->Tall.as<double>();
     } else {
-        LQ_TRY(Tloc.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
+        LQ_TRY(Tloc.alloc(c, sizeof(double) * NB_OUT * NB_OUT * (size_t)nblocks));
+        Tall = Tloc.as<double>();
+    }
+    LQ_CUDA(c, cudaMemsetAsync(Tall, 0, sizeof(double) * NB_OUT * NB_OUT * (size_t)nblocks, s_main));
+    EventPool pool;
+    cudaEvent_t ev_rest_prev = nullptr;  // completion of the side stream's last trailing update
+    if (lookahead) {
+        // the scratch buffers of the side stream come from the main stream's pool allocation
+        cudaEvent_t e0;
+        LQ_TRY(pool.make(c, &e0));
+        LQ_CUDA(c, cudaEventRecord(e0, s_main));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_side, e0, 0));
     }
     for (int blk = 0; blk < nblocks; ++blk) {
         const int k0 = blk * NB_OUT;
         const int kb = std::min(NB_OUT, npad - k0);  // multiple of 32
         const int mk = m - k0;
-        double* Tblk = keep ? keep->Tall.as<double>() + (size_t)blk * NB_OUT * NB_OUT : Tloc.as<double>();
-        if (mk <= 0) {
-            LQ_CUDA(c, cudaMemsetAsync(Tblk, 0, sizeof(double) * NB_OUT * NB_OUT, c->stream));
-            continue;
-        }
+        double* Tblk = Tall + (size_t)blk * NB_OUT * NB_OUT;
+        if (mk <= 0) continue;
         const int nin = kb / NB_IN;
-        LQ_CUDA(c, cudaMemsetAsync(Tblk, 0, sizeof(double) * NB_OUT * NB_OUT, c->stream));
         for (int ip = 0; ip < nin; ++ip) {
             const int c0 = k0 + ip * NB_IN;
             const int mp = m - c0;
@@ -382,13 +424,42 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             LQ_COUNT_LAUNCH(c);
         }
         const int ntr = npad - (k0 + kb);
-        if (ntr > 0)
-            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, A + (size_t)k0 * lda + k0 + kb, lda, ntr,
-                                         W.as<double>(), W2.as<double>()));
-        if (B && nrhs_pad > 0)
-            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
-                                         W.as<double>(), W2.as<double>()));
+        double* Ctr = A + (size_t)k0 * lda + k0 + kb;
+        if (!lookahead) {
+            if (ntr > 0)
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, ntr, W.as<double>(),
+                                             W2.as<double>()));
+            if (B && nrhs_pad > 0)
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
+                                             W.as<double>(), W2.as<double>()));
+            continue;
+        }
+        const int nnext = std::min(NB_OUT, ntr);
+        const int nrest = ntr - nnext;
+        cudaEvent_t ev_panel;
+        LQ_TRY(pool.make(c, &ev_panel));
+        LQ_CUDA(c, cudaEventRecord(ev_panel, s_main));
+        if (nnext > 0) {
+            if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
+            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
+                                         W2.as<double>()));
+        }
+        if (nrest > 0 || (B && nrhs_pad > 0)) {
+            StreamScope side(c, s_side);
+            LQ_CUDA(c, cudaStreamWaitEvent(s_side, ev_panel, 0));
+            if (nrest > 0)
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr + nnext, lda, nrest,
+                                             Ws.as<double>(), W2s.as<double>()));
+            if (B && nrhs_pad > 0)
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
+                                             Ws.as<double>(), W2s.as<double>()));
+            cudaEvent_t ev_rest;
+            LQ_TRY(pool.make(c, &ev_rest));
+            LQ_CUDA(c, cudaEventRecord(ev_rest, s_side));
+            ev_rest_prev = ev_rest;
+        }
     }
+    if (lookahead && ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));  // join
     return LQ_OK;
 }
 
