@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -300,12 +300,13 @@ def main():
 
     sampler = ClockSampler(info.local_rank)
     sampler.start()
+    time.sleep(0.3)          # let the sampler produce its first rows
+    c0 = sampler.mark()      # clocks are sampled from the warm-up through the timed region (it lasts only ~0.1-0.2 s)
     for _ in range(args.warmup):
         step_hh()
     ctx.sync()
     d.barrier()
     l0 = ctx.launches()
-    c0 = sampler.mark()
     ctx.record(2)
     for _ in range(args.steps):
         step_hh()
