@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) larft_from_gram_kernel(const double* __re
 // the whole outer block, using the Gram matrix G = V^T V:  for column block b = 1 .. nblk-1
 //     T[0:R, b] = -T[0:R, 0:R] * G[0:R, b] * T[b, b],   R = 32 b
 // (the block form of LAPACK dlarft; V1 := the first R reflectors).  One CTA, everything in shared memory.
-__global__ void __launch_bounds__(256) merge_t_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T, int ldt,
+__global__ void __launch_bounds__(1024) merge_t_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T, int ldt,
                                                       int kb) {
     extern __shared__ double sh[];
     double* Ts = sh;               // [128][129]
@@ -323,8 +323,8 @@ inline int grid_for(Ctx* c, long long total) {
 int apply_block_reflector(Ctx* c, const double* V, int ldv, const double* T, int ldt, bool trans_t, int mk, int kb,
                           double* Cm, int ldc, int nc, double* W, double* W2) {
     if (nc <= 0 || kb <= 0 || mk <= 0) return LQ_OK;
-    LQ_TRY(gemm(c, true, false, kb, nc, mk, 1.0, V, ldv, Cm, ldc, 0.0, W, nc));           // W  = V^T C
-    LQ_TRY(gemm(c, trans_t, false, kb, nc, kb, 1.0, T, ldt, W, nc, 0.0, W2, nc));          // W2 = op(T) W
+    (void)W;
+    LQ_TRY(gemm_vtc_apply_t(c, kb, nc, mk, V, ldv, Cm, ldc, T, ldt, trans_t, W2));         // W2 = op(T) (V^T C)
     LQ_TRY(gemm(c, false, false, mk, nc, kb, -1.0, V, ldv, W2, nc, 1.0, Cm, ldc));         // C -= V W2
     return LQ_OK;
 }
@@ -418,8 +418,13 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         }
         const double* Vb = V + (size_t)k0 * ldv + k0;
         if (nin > 1) {
-            LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT));
-            merge_t_kernel<<<1, 256, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
+            int grc = LQ_ERR_UNSUPPORTED;
+            if (kb == NB_OUT && getenv("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, kb, mk, Vb, ldv, Vb, ldv))
+                grc = vtc_cluster(c, 0, kb, kb, mk, Vb, ldv, Vb, ldv, nullptr, 0, G.as<double>());  // G = V^T V
+            if (grc == LQ_ERR_UNSUPPORTED)
+                grc = gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT);
+            LQ_TRY(grc);
+            merge_t_kernel<<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
             LQ_CHECK_LAUNCH(c);
             LQ_COUNT_LAUNCH(c);
         }

@@ -338,9 +338,15 @@ int launch_generic(Ctx* c, long long M, int N, int K, double alpha, const double
     return LQ_OK;
 }
 
+// when `parts` is given, the split-K partial sums are left in a workspace for a fused consumer kernel
+struct Partials {
+    DevBuf ws;
+    int splits = 1;
+    long long stride = 0;
+};
 template <bool AT, bool BT>
 int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const double* A, int lda, const double* B, int ldb,
-                double beta, double* C, int ldc) {
+                double beta, double* C, int ldc, Partials* parts = nullptr) {
     auto kern = gemm_dmma_kernel<AT, BT>;
     static bool configured[64] = {};
     if (!configured[c->device]) {
@@ -372,12 +378,14 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     GemmArgs g;
     g.A = A; g.B = B; g.M = M; g.N = N; g.K = Kmain; g.lda = lda; g.ldb = ldb;
     g.alpha = alpha; g.beta = beta; g.splits = splits;
-    DevBuf ws;
-    if (splits == 1) {
+    DevBuf ws_local;
+    DevBuf& ws = parts ? parts->ws : ws_local;
+    if (splits == 1 && !parts) {
         g.C = C; g.ldc = ldc; g.split_stride = 0;
     } else {
         LQ_TRY(ws.alloc(c, (size_t)splits * M * N * sizeof(double)));
         g.C = ws.as<double>(); g.ldc = N; g.split_stride = M * (long long)N;
+        if (splits == 1) { g.alpha = 1.0; g.beta = 0.0; }  // raw product into the workspace
     }
     CUtensorMap mapA, mapB;
     memset(&mapA, 0, sizeof(mapA));
@@ -388,6 +396,11 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, c->stream>>>(g, mapA, mapB);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
+    if (parts) {
+        parts->splits = splits;
+        parts->stride = g.split_stride;
+        return LQ_OK;
+    }
     if (splits > 1) {
         const long long total = M * N;
         const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
@@ -399,6 +412,76 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// W2 (kb x nc) = op(T) * (sum_z P_z),  P_z (kb x nc) the split-K partials of V^T C;  kb <= 128.
+// CTA b owns 32 columns.  op(T) is staged in shared memory as Ts[k][i] = op(T)[i][k], the summed partials as
+// Ws[k][c]; thread (c = tid & 31, row group tid >> 5) forms 4 outputs at a time so that every Ws load feeds 4 FMAs.
+__global__ void __launch_bounds__(1024) reduce_apply_t_kernel(const double* __restrict__ P, int splits, long long stride,
+                                                             int kb, int nc, const double* __restrict__ T, int ldt,
+                                                             int trans_t, double* __restrict__ W2) {
+    extern __shared__ double sh_rat[];
+    const int pt = kb + 1;
+    double* Ts = sh_rat;                 // [kb][kb + 1]
+    double* Ws = sh_rat + kb * pt;       // [kb][33]
+    const int c0 = blockIdx.x * 32;
+    const int ncv = min(32, nc - c0);
+    const int NT = blockDim.x;  // 1024
+    // stage op(T): 4 independent global loads in flight per thread
+    for (int e0 = threadIdx.x; e0 < kb * kb; e0 += NT * 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            const int r = e / kb, q = e - r * kb;
+            v[u] = (e < kb * kb && q >= r) ? T[(long long)r * ldt + q] : 0.0;  // T is upper triangular
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * NT;
+            if (e < kb * kb) {
+                const int r = e / kb, q = e - r * kb;
+                if (trans_t) Ts[r * pt + q] = v[u];   // op(T)[i][k] = T[k][i]  ->  Ts[k = r][i = q]
+                else Ts[q * pt + r] = v[u];           // op(T)[i][k] = T[i][k]  ->  Ts[k = q][i = r]
+            }
+        }
+    }
+    // sum the split-K partials of my 32 columns: thread (k = tid >> 5 (+32, ...), cc = tid & 31), 8 splits in flight
+    {
+        const int cc = threadIdx.x & 31;
+        const bool ok = cc < ncv;
+        for (int k = threadIdx.x >> 5; k < kb; k += NT / 32) {
+            double sa[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            const double* src = P + (long long)k * nc + c0 + cc;
+            if (ok) {
+                int z = 0;
+                for (; z + 8 <= splits; z += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sa[u] += src[(z + u) * stride];
+                }
+                for (; z < splits; ++z) sa[0] += src[z * stride];
+            }
+            Ws[k * 33 + cc] = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
+        }
+    }
+    __syncthreads();
+    const int cc = threadIdx.x & 31;
+    for (int i0 = (threadIdx.x >> 5) * 4; i0 < kb; i0 += NT / 8) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        // op(T)[i][k] != 0 only for k <= i (transpose) or k >= i (no transpose)
+        const int klo = trans_t ? 0 : i0;
+        const int khi = trans_t ? min(kb, i0 + 4) : kb;
+        for (int k = klo; k < khi; ++k) {
+            const double w = Ws[k * 33 + cc];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fma(Ts[k * pt + i0 + r], w, acc[r]);
+        }
+        if (cc < ncv) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i0 + r < kb) W2[(long long)(i0 + r) * nc + c0 + cc] = acc[r];
+        }
+    }
+}
 
 }  // namespace
 
@@ -438,6 +521,40 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
         if (tb) return launch_generic<false, true>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
         return launch_generic<false, false>(c, M, N, Kr, alpha, A2, lda, B2, ldb, 1.0, C, ldc);
     }
+    return LQ_OK;
+}
+
+// W2 (kb x nc, ld nc) = op(T) * (V^T C):  V (mk x kb, ldv), C (mk x nc, ldc), T (kb x kb upper, ldt), kb <= 128.
+// One split-K tensor-core GEMM whose partial sums feed a fused reduce + triangular-multiply kernel.
+int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
+                     int ldt, bool trans_t, double* W2) {
+    if (kb <= 0 || nc <= 0) return LQ_OK;
+    if (getenv("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, nc, mk, V, ldv, Cm, ldc)) {
+        const int rc = vtc_cluster(c, trans_t ? 1 : 2, kb, nc, mk, V, ldv, Cm, ldc, T, ldt, W2);
+        if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    }
+    const int Kmain = mk - mk % BK;
+    const bool fast = kb <= 128 && Kmain >= BK && Kmain == mk && aligned16(V) && aligned16(Cm) && (ldv % 2 == 0) &&
+                      (ldc % 2 == 0) && (kb % 4 == 0) && (nc % 2 == 0) && !getenv("LINALG_B200_NO_FAST_GEMM");
+    if (!fast) {
+        DevBuf W;
+        LQ_TRY(W.alloc(c, sizeof(double) * (size_t)kb * nc));
+        LQ_TRY(gemm(c, true, false, kb, nc, mk, 1.0, V, ldv, Cm, ldc, 0.0, W.as<double>(), nc));
+        return gemm(c, trans_t, false, kb, nc, kb, 1.0, T, ldt, W.as<double>(), nc, 0.0, W2, nc);
+    }
+    Partials parts;
+    LQ_TRY((launch_fast<true, false>(c, kb, nc, Kmain, 1.0, V, ldv, Cm, ldc, 0.0, nullptr, nc, &parts)));
+    const size_t rat_smem = ((size_t)kb * (kb + 1) + (size_t)kb * 33 + 8) * sizeof(double);
+    static bool rat_configured[64] = {};
+    if (!rat_configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(reduce_apply_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((128 * 129 + 128 * 33 + 8) * sizeof(double))));
+        rat_configured[c->device] = true;
+    }
+    reduce_apply_t_kernel<<<(nc + 31) / 32, 1024, rat_smem, c->stream>>>(parts.ws.as<double>(), parts.splits, parts.stride, kb,
+                                                                       nc, T, ldt, trans_t ? 1 : 0, W2);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
     return LQ_OK;
 }
 
