@@ -216,9 +216,70 @@ __global__ void __launch_bounds__(256) scale_cols_kernel(double* __restrict__ M,
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) M[e] *= sgn[e % n];
 }
 
+// Upper Cholesky factor R (R^T R = G) of an n x n (n <= 128) SPD matrix, one CTA, right-looking in shared memory.
+// stat[0] = 1 if a pivot is not safely positive (breakdown), stat[1] = max_j G_jj / min_j R_jj^2  (~ cond(A)^2).
+__global__ void __launch_bounds__(1024) chol_upper_kernel(const double* __restrict__ G, int n, double* __restrict__ R,
+                                                          double* __restrict__ stat) {
+    extern __shared__ double chol_sm[];
+    double (*S)[129] = reinterpret_cast<double (*)[129]>(chol_sm);
+    __shared__ double s_dmax, s_pmin;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < n * n; e += nt) S[e / n][e % n] = G[e];
+    if (tid == 0) {
+        s_dmax = 0.0;
+        s_pmin = 1e300;
+        s_bad = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double dm = 0.0;
+        for (int j = 0; j < n; ++j) dm = fmax(dm, S[j][j]);
+        s_dmax = dm;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        const double piv = S[j][j];
+        if (!(piv > 0.0)) {  // also catches NaN
+            if (tid == 0) s_bad = 1;
+            break;           // uniform: every thread reads the same S[j][j]
+        }
+        const double d = sqrt(piv);
+        __syncthreads();
+        if (tid == 0) s_pmin = fmin(s_pmin, piv);
+        for (int cidx = j + tid; cidx < n; cidx += nt) S[j][cidx] = (cidx == j) ? d : S[j][cidx] / d;
+        __syncthreads();
+        const int rem = n - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int i = j + 1 + e / rem, cidx = j + 1 + e % rem;
+            if (cidx >= i) S[i][cidx] = fma(-S[j][i], S[j][cidx], S[i][cidx]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, cidx = e % n;
+        R[e] = (cidx >= i) ? S[i][cidx] : 0.0;
+    }
+    if (tid == 0) {
+        stat[0] = s_bad ? 1.0 : 0.0;
+        stat[1] = s_bad ? 1e300 : s_dmax / s_pmin;
+    }
+}
+
+constexpr size_t CHOL_SMEM = 128 * 129 * sizeof(double);
+
+__global__ void __launch_bounds__(256) scale_cols_tall_kernel(double* __restrict__ M, long long rows, int n,
+                                                              const double* __restrict__ sgn) {
+    const long long total = rows * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        M[e] *= sgn[e % n];
+}
+
 int eigh_configure(Ctx* c) {
     static bool done[64] = {};
     if (done[c->device]) return LQ_OK;
+    LQ_CUDA(c, cudaFuncSetAttribute(chol_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
     cudaFuncAttributes fa{};
     LQ_CUDA(c, cudaFuncGetAttributes(&fa, jacobi_kernel));
     LQ_CUDA(c, cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -326,10 +387,7 @@ int svd_gram_local(Ctx* c, const double* A, long long m, int n, double tol, doub
 // TSQR: R by a Householder reduction tree (leaves stream their rows, R factors are combined),
 // Q = A R^{-1} followed by one TSQR refinement pass (restores orthogonality to O(eps) whenever
 // cond(A) * eps << 1), signs normalised so that diag(R) > 0 -- the MGS convention (qr.py:39-42).
-int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
-    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "tsqr needs m >= n >= 1 (got %lld x %d)", m, n);
-    LQ_REQUIRE(c, n <= 128, LQ_ERR_UNSUPPORTED, "tsqr supports n <= 128 (got %d); use householder_qr", n);
-    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "tsqr: more than 2^31 rows per device not supported");
+static int tsqr_householder(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
     LQ_TRY(eigh_configure(c));
     DevBuf R1, R2, Rinv, Rall, sgn, Q1;
     const size_t nn = sizeof(double) * (size_t)n * n;
@@ -370,6 +428,79 @@ int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R
     c->launches += 5;
     LQ_TRY(gemm(c, false, false, m, n, n, 1.0, Q1.as<double>(), n, Rinv.as<double>(), n, 0.0, Q, n));
     return LQ_OK;
+}
+
+// Fast path for well-conditioned tall-skinny matrices: CholeskyQR2 on the FP64 tensor pipe.
+//   G1 = A^T A (+ all-reduce over the row shards) -> R1 = chol(G1) -> Q1 = A R1^{-1}
+//   G2 = Q1^T Q1 (+ all-reduce)                   -> R2 = chol(G2) -> Q  = Q1 R2^{-1},  R = R2 R1
+// Four streaming GEMMs instead of two column-by-column Householder sweeps; diag(R) > 0 by construction (the
+// convention of linalg/qr.py:39-42).  The second pass restores orthogonality to O(eps) as long as
+// cond(A)^2 * eps << 1; the Cholesky kernel reports a cond(A)^2 estimate and the Householder TSQR tree below
+// takes over when it exceeds 1e10 (or a pivot breaks down).  *used = 0 means "fall back".
+static int tsqr_cholqr2(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded, int* used) {
+    *used = 0;
+    LQ_TRY(eigh_configure(c));
+    DevBuf G, R1, R2, Rinv, Q1, stat;
+    const size_t nn = sizeof(double) * (size_t)n * n;
+    LQ_TRY(G.alloc(c, nn));
+    LQ_TRY(R1.alloc(c, nn));
+    LQ_TRY(R2.alloc(c, nn));
+    LQ_TRY(Rinv.alloc(c, nn));
+    LQ_TRY(stat.alloc(c, 4 * sizeof(double)));
+    double hstat[4] = {0, 0, 0, 0};
+    // pass 1
+    LQ_TRY(gram(c, A, m, n, G.as<double>()));
+    if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
+    chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    LQ_CUDA(c, cudaMemcpyAsync(hstat, stat.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hstat[0] != 0.0 || !(hstat[1] < 1e10)) return LQ_OK;  // ill-conditioned: caller falls back (same on every rank)
+    LQ_TRY(Q1.alloc(c, sizeof(double) * (size_t)m * n));
+    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R1.as<double>(), n, Rinv.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, Rinv.as<double>(), n, 0.0, Q1.as<double>(), n));
+    // pass 2
+    LQ_TRY(gram(c, Q1.as<double>(), m, n, G.as<double>()));
+    if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
+    chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
+    LQ_CHECK_LAUNCH(c);
+    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R2.as<double>(), n, Rinv.as<double>());
+    LQ_CHECK_LAUNCH(c);
+    c->launches += 3;
+    LQ_TRY(gemm(c, false, false, n, n, n, 1.0, R2.as<double>(), n, R1.as<double>(), n, 0.0, R, n));
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, Q1.as<double>(), n, Rinv.as<double>(), n, 0.0, Q, n));
+    *used = 1;
+    return LQ_OK;
+}
+
+// a7: thin QR of a tall-skinny matrix with diag(R) > 0.
+int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
+    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "tsqr needs m >= n >= 1 (got %lld x %d)", m, n);
+    LQ_REQUIRE(c, n <= 128, LQ_ERR_UNSUPPORTED, "tsqr supports n <= 128 (got %d); use householder_qr", n);
+    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "tsqr: more than 2^31 rows per device not supported");
+    const bool sh = sharded && c->nranks > 1;
+    if (!getenv("LINALG_B200_TSQR_HOUSEHOLDER") && m >= 4LL * n) {
+        int used = 0;
+        LQ_TRY(tsqr_cholqr2(c, A, m, n, Q, R, sh, &used));
+        if (used) return LQ_OK;
+    }
+    if (!sh) {
+        // robust path for ill-conditioned (or nearly square) input: the blocked compact-WY Householder QR, whose
+        // Q is formed from the reflectors (residual and orthogonality O(eps) for any cond(A)), flipped to diag(R) > 0
+        DevBuf sgn;
+        LQ_TRY(sgn.alloc(c, sizeof(double) * n));
+        LQ_TRY(blocked_householder_qr(c, A, (int)m, n, Q, R));
+        sign_fix_R_kernel<<<1, 256, 0, c->stream>>>(R, n, sgn.as<double>());
+        scale_cols_tall_kernel<<<grid_for(c, m * n), 256, 0, c->stream>>>(Q, m, n, sgn.as<double>());
+        LQ_CHECK_LAUNCH(c);
+        c->launches += 2;
+        return LQ_OK;
+    }
+    // row-sharded and ill-conditioned: Householder reduction tree + Q = A R^{-1} with one refinement pass
+    // (orthogonality O(eps), residual O(cond(A) eps))
+    return tsqr_householder(c, A, m, n, Q, R, sharded);
 }
 
 }  // namespace lq

@@ -382,6 +382,15 @@ def test_tsqr_shapes(ctx, m, n):
     assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
 
 
+def test_tsqr_ill_conditioned_falls_back_to_householder(ctx):
+    """cond(A) ~ 1e9+: the CholeskyQR2 fast path must hand over to the reflector-based path and stay O(eps)."""
+    A = np.random.default_rng(3).standard_normal((20000, 32)) * np.logspace(0, -9, 32)
+    A[:, 5] = A[:, 4] * (1 + 1e-9) + 1e-9 * A[:, 6]
+    Q, R = lb.tsqr(A, ctx=ctx)
+    assert np.all(np.diag(R) > 0) and np.all(np.tril(R, -1) == 0.0)
+    assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
+
+
 def test_no_cpu_fallback_loaded(ctx):
     """The numbers above came from the in-tree CUDA library: it is the loaded object and it counted launches."""
     from linalg_b200 import _native
