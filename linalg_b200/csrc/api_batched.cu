@@ -33,7 +33,7 @@ static int launch_mgs32(Ctx* c, cudaStream_t st, const double* A, long long batc
                         int* info) {
     using D = Dist32<P, C>;
     auto kern = mgs_qr32_kernel<P, C, WARPS, MINB>;
-    const size_t smem = (size_t)WARPS * D::MPW * 64 * sizeof(double);
+    const size_t smem = (size_t)WARPS * D::MPW * D::MGS_DOUBLES * sizeof(double);
     const long long per_block = (long long)WARPS * D::MPW;
     const long long blocks = (batch + per_block - 1) / per_block;
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, info, batch, reorth);
@@ -87,7 +87,10 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
 int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long batch, int m, int n, int reorth,
                           double* Q, double* R, int* info) {
     if (batch == 0) return LQ_OK;
-    if (m == 32 && n == 32) return launch_mgs32<2, 4, 2, 6>(c, st, A, batch, reorth, Q, R, info);
+    if (m == 32 && n == 32) {
+        if (getenv("LINALG_B200_MGS_MINB6")) return launch_mgs32<2, 4, 2, 6>(c, st, A, batch, reorth, Q, R, info);
+        return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);
+    }
     const size_t smem = small_mgs_smem_doubles(m, n, 0) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
         static bool configured[64] = {};

@@ -34,6 +34,7 @@ struct Dist32 {
     static constexpr int PSTRIDE = RPL + (P > 1 ? 2 : 0);   // doubles between the p sub-rows
     static constexpr int ROWP = P * PSTRIDE;                // doubles per reflector row
     static constexpr int SMEM_DOUBLES = N * ROWP + 2 * N + 4;
+    static constexpr int MGS_DOUBLES = 2 * ROWP + (P > 1 ? 4 : 0);  // MGS: two alternating reflector rows per matrix
     __device__ __host__ static constexpr int col(int s, int lc) {
         return (s & 1) ? ((s + 1) * LC - 1 - lc) : (s * LC + lc);
     }
@@ -278,8 +279,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     const long long mat = ((long long)blockIdx.x * WARPS + warp) * D::MPW + g;
     const bool valid = mat < batch;
     const long long matc = valid ? mat : (batch - 1);
-    // scratch: two alternating 32-double rows per matrix
-    double* vb = smem + (size_t)(warp * D::MPW + g) * (2 * N);
+    // scratch: two alternating column buffers per matrix; the (matrix, row-lane) groups of a warp are
+    // staggered by 4 banks like in the Householder kernel (un-staggered they collide 4-way on every LDS.128)
+    double* vb = smem + (size_t)(warp * D::MPW + g) * D::MGS_DOUBLES;
 
     int colv[C];
 #pragma unroll
@@ -303,27 +305,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const int so = D::owner_slot(j), lo = D::owner_lc(j);
-            double* vj = vb + (j & 1) * N + p * RPL;
+            double* vj = vb + (j & 1) * D::ROWP + p * D::PSTRIDE;
             if (lc == lo) {
 #pragma unroll
                 for (int ii = 0; ii < RPL; ii += 2)
                     *reinterpret_cast<double2*>(vj + ii) = make_double2(a[so][ii], a[so][ii + 1]);
             }
             __syncwarp();
-            double d[C];
+            double d[C], d2[C], vk[RPL];
 #pragma unroll
-            for (int s = 0; s < C; ++s) d[s] = 0.0;
+            for (int s = 0; s < C; ++s) d[s] = 0.0, d2[s] = 0.0;
 #pragma unroll
             for (int ii = 0; ii < RPL; ii += 2) {
                 const double2 vv = *reinterpret_cast<const double2*>(vj + ii);
+                vk[ii] = vv.x;
+                vk[ii + 1] = vv.y;
 #pragma unroll
                 for (int s = so; s < C; ++s) {
                     d[s] = fma(vv.x, a[s][ii], d[s]);
-                    d[s] = fma(vv.y, a[s][ii + 1], d[s]);
+                    d2[s] = fma(vv.y, a[s][ii + 1], d2[s]);
                 }
             }
 #pragma unroll
-            for (int s = so; s < C; ++s) d[s] = group_sum<P, C>(d[s]);
+            for (int s = so; s < C; ++s) d[s] = group_sum<P, C>(d[s] + d2[s]);
             const double ss = __shfl_sync(0xffffffffu, d[so], lo, L);  // ||v_j||^2
             double rinv;
             const double nrm = sqrt_nr(fmax(ss, 1e-300), rinv);
@@ -346,13 +350,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 if (c == j) rinvn[s] = rinv;
             }
 #pragma unroll
-            for (int ii = 0; ii < RPL; ii += 2) {
-                const double2 vv = *reinterpret_cast<const double2*>(vj + ii);
+            for (int ii = 0; ii < RPL; ++ii) {
 #pragma unroll
-                for (int s = so; s < C; ++s) {
-                    a[s][ii] = fma(-d[s], vv.x, a[s][ii]);
-                    a[s][ii + 1] = fma(-d[s], vv.y, a[s][ii + 1]);
-                }
+                for (int s = so; s < C; ++s) a[s][ii] = fma(-d[s], vk[ii], a[s][ii]);
             }
         }
         // normalise: q_c = v_c / ||v_c||
