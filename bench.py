@@ -139,7 +139,7 @@ def _cpu_worker(args):
     raise ValueError(kind)
 
 
-def cpu_baseline_hh32(per_worker=1536, workers=None, steps=1, warmup=0):
+def cpu_baseline_hh32(per_worker=16384, workers=None, steps=1, warmup=0):
     """The reference's algorithm (NumPy oracle port, linalg/qr.py:52-100) over all host cores:
     one process per core, BLAS pinned to 1 thread each.  One "step" factors
     ``per_worker * workers`` matrices; returns the mean throughput of the timed steps."""
@@ -179,7 +179,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_worker = 512
+    per_worker = 1024   # x cores matrices per step; the default 20 + 5 steps then take ~15-20 s
     base = cpu_baseline_hh32(per_worker=per_worker, steps=args.steps, warmup=args.warmup)
     value = base["value"]
     line = {

@@ -152,6 +152,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
+    // read-modify-write epilogue ahead: pull my part of the C tile into L2 while the main loop runs
+    if (g.splits == 1 && g.beta != 0.0) {
+#pragma unroll
+        for (int im = 0; im < 4; ++im)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = wm * 64 + im * 16 + gq + half * 8;
+                if (r < mvalid && tq == 0) {
+                    const double* crow = g.C + (m0 + r) * (long long)g.ldc + n0 + wn * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(crow));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16));
+                }
+            }
+    }
+
     for (int it = 0; it < nkt; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;

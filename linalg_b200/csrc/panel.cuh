@@ -128,10 +128,20 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1)
                 }
             }
         }
+        {
+            double dB[C];  // second accumulator per column slot: halves the dependent DFMA chains
 #pragma unroll
-        for (int ii = 0; ii < RPT; ++ii)
+            for (int s = 0; s < C; ++s) dB[s] = 0.0;
 #pragma unroll
-            for (int s = 0; s < C; ++s) d[s] = fma(xv[ii], r[s][ii], d[s]);
+            for (int ii = 0; ii < RPT; ii += 2)
+#pragma unroll
+                for (int s = 0; s < C; ++s) {
+                    d[s] = fma(xv[ii], r[s][ii], d[s]);
+                    dB[s] = fma(xv[ii + 1], r[s][ii + 1], dB[s]);
+                }
+#pragma unroll
+            for (int s = 0; s < C; ++s) d[s] += dB[s];
+        }
         // combine the 4 row lanes
 #pragma unroll
         for (int s = 0; s < C; ++s) {
@@ -171,16 +181,30 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1)
         cluster_sync_all();
 
         // ---- every warp forms the totals for its columns: lane c holds column c
-        double tot = 0.0;
-        for (int t = 0; t < CS; ++t) tot += sm.recv[par][t][lane];
+        double tot;
+        {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;  // CS is 1, 2, 4, 8 or 16
+            if (CS >= 4) {
+                for (int t = 0; t < CS; t += 4) {
+                    t0 += sm.recv[par][t][lane];
+                    t1 += sm.recv[par][t + 1][lane];
+                    t2 += sm.recv[par][t + 2][lane];
+                    t3 += sm.recv[par][t + 3][lane];
+                }
+            } else {
+                for (int t = 0; t < CS; ++t) t0 += sm.recv[par][t][lane];
+            }
+            tot = (t0 + t1) + (t2 + t3);
+        }
         const double prow = sm.precv[par][lane];
         const double ss = __shfl_sync(0xffffffffu, tot, j);    // sum_{r>=j} x_r^2
         const double x0 = __shfl_sync(0xffffffffu, prow, j);   // pivot
-        const double nrm = sqrt(fmax(ss, 0.0));
+        double rinv_n;
+        const double nrm = sqrt_nr(fmax(ss, 1e-300), rinv_n);  // MUFU seed + Newton steps, full double accuracy
         const bool skip = nrm < kEps;  // qr.py:79-80
         const double alpha = copysign(nrm, x0);
         const double v0 = x0 + alpha;
-        const double beta = skip ? 0.0 : 1.0 / (nrm * fabs(v0));
+        const double beta = skip ? 0.0 : rcp_nr(nrm * fabs(v0));
         // g_c = v^T P[:, c] = x^T P[:, c] + alpha * P[j][c]
         const double gl = fma(alpha, prow, tot);
         double sc[C];
@@ -213,8 +237,16 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1)
             // T_u[0:j, j] = -beta * T_u[0:j, 0:j] * g[0:j],  T_u[j][j] = beta
             sm.gbuf[lane] = gl;
             __syncwarp();
-            double acc = 0.0;
-            for (int k = 0; k < j; ++k) acc = fma(sm.Tt[k][lane], sm.gbuf[k], acc);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= j; k += 4) {
+                a0 = fma(sm.Tt[k][lane], sm.gbuf[k], a0);
+                a1 = fma(sm.Tt[k + 1][lane], sm.gbuf[k + 1], a1);
+                a2 = fma(sm.Tt[k + 2][lane], sm.gbuf[k + 2], a2);
+                a3 = fma(sm.Tt[k + 3][lane], sm.gbuf[k + 3], a3);
+            }
+            for (; k < j; ++k) a0 = fma(sm.Tt[k][lane], sm.gbuf[k], a0);
+            const double acc = (a0 + a1) + (a2 + a3);
             __syncwarp();
             if (lane < j) sm.Tt[j][lane] = -beta * acc;
             if (lane == j) sm.Tt[j][lane] = beta;
