@@ -478,10 +478,10 @@ int configure_once(Ctx* c) {
     return LQ_OK;
 }
 
-// back-substitution  R X = Y  for an upper-triangular R (n x n, ldr) and Y (n x k, ldy) in place; one CTA.
+// back-substitution  R X = Y  for an upper-triangular R (n x n, ldr) and Y (n x k, ldy) in place.
+// Small systems: one thread per right-hand side.
 __global__ void __launch_bounds__(256) backsub_kernel(const double* __restrict__ R, int ldr, double* __restrict__ Y, int ldy,
                                                       int n, int k) {
-    // column-parallel: thread t owns right-hand side t (looped), rows solved bottom-up
     for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < k; col += gridDim.x * blockDim.x) {
         for (int i = n - 1; i >= 0; --i) {
             double acc = Y[(long long)i * ldy + col];
@@ -489,6 +489,67 @@ __global__ void __launch_bounds__(256) backsub_kernel(const double* __restrict__
             Y[(long long)i * ldy + col] = acc / R[(long long)i * ldr + i];
         }
     }
+}
+// One diagonal block (nb <= 128 rows) of a blocked back-substitution: Rbb in shared memory, CTA b solves a chunk
+// of 32 right-hand sides; per row one divide, then a rank-1 update of the rows above by all threads.
+__global__ void __launch_bounds__(256) backsub_diag_kernel(const double* __restrict__ R, int ldr, double* __restrict__ Y,
+                                                           int ldy, int nb, int k) {
+    extern __shared__ double bs_sm[];
+    double* Rs = bs_sm;               // [nb][129]
+    double* Ys = bs_sm + 128 * 129;   // [nb][33]
+    __shared__ double xrow[32];
+    const int c0 = blockIdx.x * 32, kc = min(32, k - c0);
+    for (int e = threadIdx.x; e < nb * nb; e += 256) Rs[(e / nb) * 129 + e % nb] = R[(long long)(e / nb) * ldr + e % nb];
+    for (int e = threadIdx.x; e < nb * 32; e += 256) {
+        const int i = e >> 5, cc = e & 31;
+        Ys[i * 33 + cc] = (cc < kc) ? Y[(long long)i * ldy + c0 + cc] : 0.0;
+    }
+    __syncthreads();
+    for (int i = nb - 1; i >= 0; --i) {
+        if (threadIdx.x < 32) {
+            const double x = Ys[i * 33 + threadIdx.x] / Rs[i * 129 + i];
+            xrow[threadIdx.x] = x;
+            Ys[i * 33 + threadIdx.x] = x;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < i * 32; e += 256) {
+            const int r = e >> 5, cc = e & 31;
+            Ys[r * 33 + cc] = fma(-Rs[r * 129 + i], xrow[cc], Ys[r * 33 + cc]);
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < nb * 32; e += 256) {
+        const int i = e >> 5, cc = e & 31;
+        if (cc < kc) Y[(long long)i * ldy + c0 + cc] = Ys[i * 33 + cc];
+    }
+}
+constexpr size_t BACKSUB_SMEM = (128 * 129 + 128 * 33) * sizeof(double);
+
+// R X = Y in place (Y: n x k, ldy; k even when the tensor-core GEMM is to be used for the off-diagonal part)
+int back_substitute(Ctx* c, const double* R, int ldr, double* Y, int ldy, int n, int k) {
+    if (n <= 256) {
+        backsub_kernel<<<std::max(1, (k + 255) / 256), 256, 0, c->stream>>>(R, ldr, Y, ldy, n, k);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+        return LQ_OK;
+    }
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(backsub_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACKSUB_SMEM));
+        configured[c->device] = true;
+    }
+    const int nblk = (n + 127) / 128;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int r0 = b * 128, nb = std::min(128, n - r0), after = n - (r0 + nb);
+        if (after > 0)  // Y_b -= R[b, after] X[after]
+            LQ_TRY(gemm(c, false, false, nb, k, after, -1.0, R + (size_t)r0 * ldr + r0 + nb, ldr, Y + (size_t)(r0 + nb) * ldy, ldy,
+                        1.0, Y + (size_t)r0 * ldy, ldy));
+        backsub_diag_kernel<<<(k + 31) / 32, 256, BACKSUB_SMEM, c->stream>>>(R + (size_t)r0 * ldr + r0, ldr, Y + (size_t)r0 * ldy,
+                                                                            ldy, nb, k);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+    }
+    return LQ_OK;
 }
 
 }  // namespace
@@ -537,7 +598,8 @@ int blocked_householder_qr(Ctx* c, const double* A, int m, int n, double* Q, dou
     set_identity_kernel<<<grid_for(c, (long long)m * ldq), 256, 0, c->stream>>>(Qp, ldq, m, ldq);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
-    for (int blk = keep.nblocks - 1; blk >= 0; --blk) {
+    const bool skip_q = getenv("LINALG_B200_DEBUG_SKIP_Q") != nullptr;  // timing experiments only (Q = I)
+    for (int blk = keep.nblocks - 1; blk >= 0 && !skip_q; --blk) {
         const int k0 = blk * NB_OUT;
         const int kb = std::min(NB_OUT, npad - k0);
         const int mk = m - k0;
@@ -570,9 +632,7 @@ int large_lstsq_householder(Ctx* c, const double* A, const double* B, int m, int
     c->launches += 2;
     LQ_CUDA(c, cudaMemsetAsync(Vw.p, 0, sizeof(double) * (size_t)m * npad, c->stream));
     LQ_TRY(factor_padded(c, Aw.as<double>(), npad, m, npad, n, Vw.as<double>(), npad, Bw.as<double>(), kpad, kpad, nullptr));
-    backsub_kernel<<<std::max(1, (nrhs + 255) / 256), 256, 0, c->stream>>>(Aw.as<double>(), npad, Bw.as<double>(), kpad, n, nrhs);
-    LQ_CHECK_LAUNCH(c);
-    LQ_COUNT_LAUNCH(c);
+    LQ_TRY(back_substitute(c, Aw.as<double>(), npad, Bw.as<double>(), kpad, n, kpad));
     unpad_copy_kernel<<<grid_for(c, (long long)n * nrhs), 256, 0, c->stream>>>(Bw.as<double>(), kpad, X, nrhs, n, nrhs);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);

@@ -78,12 +78,15 @@ struct GemmArgs {
 
 // AT: A is stored K x M (op(A) = A^T)  -> shared tile [k][m]   ("M-major")
 // BT: B is stored N x K (op(B) = B^T)  -> shared tile [n][k]   ("K-major")
+// 9 warps: registers are granted per 4-warp group, so a 288-thread block is capped at 168 registers/thread; the
+// main loop therefore keeps only ONE A fragment live at a time (128 accumulator + 8 + 16 fragment registers).
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_dmma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem_raw =
-        reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the swizzled TMA boxes; the offset is added to the __shared__ symbol itself so that
+    // the compiler keeps the shared address space (LDS instead of generic LD)
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     double* tiles = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * 2 * TILE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -175,23 +178,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const double* sB = sA + TILE_DOUBLES;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-            double af[4][4], bf[4][2];
+            double bf[4][2];
             const int kA = ks * 8 + tq;
-#pragma unroll
-            for (int im = 0; im < 4; ++im) {
-                const int r = wm * 64 + im * 16 + gq;
-                if (AT) {
-                    af[im][0] = sA[kA * PM + r];
-                    af[im][1] = sA[kA * PM + r + 8];
-                    af[im][2] = sA[(kA + 4) * PM + r];
-                    af[im][3] = sA[(kA + 4) * PM + r + 8];
-                } else {
-                    af[im][0] = sA[sw_idx(r, gq, kA)];
-                    af[im][1] = sA[sw_idx(r + 8, gq, kA)];
-                    af[im][2] = sA[sw_idx(r, gq, kA + 4)];
-                    af[im][3] = sA[sw_idx(r + 8, gq, kA + 4)];
-                }
-            }
 #pragma unroll
             for (int jn = 0; jn < 4; ++jn) {
                 const int c = wn * 32 + jn * 8 + gq;
@@ -204,9 +192,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 }
             }
 #pragma unroll
-            for (int im = 0; im < 4; ++im)
+            for (int im = 0; im < 4; ++im) {
+                double af[4];
+                const int r = wm * 64 + im * 16 + gq;
+                if (AT) {
+                    af[0] = sA[kA * PM + r];
+                    af[1] = sA[kA * PM + r + 8];
+                    af[2] = sA[(kA + 4) * PM + r];
+                    af[3] = sA[(kA + 4) * PM + r + 8];
+                } else {
+                    af[0] = sA[sw_idx(r, gq, kA)];
+                    af[1] = sA[sw_idx(r + 8, gq, kA)];
+                    af[2] = sA[sw_idx(r, gq, kA + 4)];
+                    af[3] = sA[sw_idx(r + 8, gq, kA + 4)];
+                }
 #pragma unroll
-                for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af[im], bf[jn]);
+                for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af, bf[jn]);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -223,43 +225,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool vec2 = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
 #pragma unroll
     for (int im = 0; im < 4; ++im) {
-        double cold[2][4][2];
-        if (beta != 0.0) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int r = wm * 64 + im * 16 + gq + half * 8;
-                const double* crow = Cb + (m0 + r) * (long long)g.ldc + n0;
-#pragma unroll
-                for (int jn = 0; jn < 4; ++jn) {
-                    const int c = wn * 32 + jn * 8 + 2 * tq;
-                    cold[half][jn][0] = 0.0;
-                    cold[half][jn][1] = 0.0;
-                    if (r < mvalid) {
-                        if (vec2 && c + 1 < nvalid) {
-                            const double2 t2 = *reinterpret_cast<const double2*>(crow + c);
-                            cold[half][jn][0] = t2.x;
-                            cold[half][jn][1] = t2.y;
-                        } else {
-                            if (c < nvalid) cold[half][jn][0] = crow[c];
-                            if (c + 1 < nvalid) cold[half][jn][1] = crow[c + 1];
-                        }
-                    }
-                }
-            }
-        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = wm * 64 + im * 16 + gq + half * 8;
             if (r >= mvalid) continue;
             double* crow = Cb + (m0 + r) * (long long)g.ldc + n0;
+            double cold[4][2];
+            if (beta != 0.0) {
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + 2 * tq;
+                    cold[jn][0] = 0.0;
+                    cold[jn][1] = 0.0;
+                    if (vec2 && c + 1 < nvalid) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(crow + c);
+                        cold[jn][0] = t2.x;
+                        cold[jn][1] = t2.y;
+                    } else {
+                        if (c < nvalid) cold[jn][0] = crow[c];
+                        if (c + 1 < nvalid) cold[jn][1] = crow[c + 1];
+                    }
+                }
+            }
 #pragma unroll
             for (int jn = 0; jn < 4; ++jn) {
                 const int c = wn * 32 + jn * 8 + 2 * tq;
                 double v0 = alpha * acc[im][jn][half * 2 + 0];
                 double v1 = alpha * acc[im][jn][half * 2 + 1];
                 if (beta != 0.0) {
-                    v0 = fma(beta, cold[half][jn][0], v0);
-                    v1 = fma(beta, cold[half][jn][1], v1);
+                    v0 = fma(beta, cold[jn][0], v0);
+                    v1 = fma(beta, cold[jn][1], v1);
                 }
                 if (vec2 && c + 1 < nvalid) {
                     *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);

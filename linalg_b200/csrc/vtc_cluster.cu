@@ -38,7 +38,7 @@ struct VtcArgs {
     int mode;  // 0: W2 = V^T C;  1: W2 = T^T (V^T C);  2: W2 = T (V^T C)
 };
 
-__global__ void __launch_bounds__(VTC_THREADS, 1) vtc_cluster_kernel(const VtcArgs g) {
+__global__ void __maxnreg__(224) vtc_cluster_kernel(const VtcArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + RING_BYTES);
