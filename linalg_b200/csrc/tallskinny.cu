@@ -35,8 +35,8 @@ __device__ __forceinline__ void rr_pair(int n_even, int round, int k, int& p, in
     q = max(a, b);
 }
 
-__global__ void __launch_bounds__(512) jacobi_kernel(const double* __restrict__ G, int n, double* __restrict__ Awork,
-                                                     int use_global, double2* __restrict__ rotlog, int max_sweeps,
+__global__ void __launch_bounds__(1024) jacobi_kernel(const double* __restrict__ G, int n, double* __restrict__ Awork,
+                                                     int use_global, double2* __restrict__ rotlog, int max_sweeps, double rel_tol,
                                                      int* __restrict__ nrounds_out, double* __restrict__ lambda) {
     extern __shared__ __align__(16) double sm[];
     const int ne = (n + 1) & ~1;          // padded to even; the pad index never rotates (zero coupling)
@@ -76,35 +76,42 @@ __global__ void __launch_bounds__(512) jacobi_kernel(const double* __restrict__ 
                 pq[kk] = make_int2(p, q);
                 const double app = Am[(size_t)p * ld + p], aqq = Am[(size_t)q * ld + q], apq = Am[(size_t)p * ld + q];
                 double cc = 1.0, ss = 0.0;
-                if (fabs(apq) > floor_abs && fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq))) {
+                if (fabs(apq) > floor_abs && fabs(apq) > rel_tol * sqrt(fabs(app * aqq))) {
                     const double tau = (aqq - app) / (2.0 * apq);
                     const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
                     cc = 1.0 / sqrt(1.0 + t * t);
                     ss = t * cc;
-                    atomicAdd(&s_rot, 1);
+                    s_rot = 1;  // benign race: every writer stores the same value (a same-address atomic serialises 64 lanes)
                 }
                 cs[kk] = make_double2(cc, ss);
                 rotlog[(size_t)rounds * half + kk] = make_double2(cc, ss);
             }
             __syncthreads();
-            // columns: A[:, p], A[:, q]
-            for (int e = tid; e < half * ne; e += nt) {
-                const int k = e / ne, i = e - k * ne;
+            // columns: A[:, p], A[:, q] -- one warp per rotation pair, lanes over the rows (no integer division)
+            const int wid = tid >> 5, ln = tid & 31, nwp = nt >> 5;
+            for (int k = wid; k < half; k += nwp) {
                 const int p = pq[k].x, q = pq[k].y;
                 const double2 r2 = cs[k];
-                const double ap = Am[(size_t)i * ld + p], aq = Am[(size_t)i * ld + q];
-                Am[(size_t)i * ld + p] = r2.x * ap - r2.y * aq;
-                Am[(size_t)i * ld + q] = r2.y * ap + r2.x * aq;
+                if (r2.y != 0.0) {
+                    for (int i = ln; i < ne; i += 32) {
+                        const double ap = Am[(size_t)i * ld + p], aq = Am[(size_t)i * ld + q];
+                        Am[(size_t)i * ld + p] = r2.x * ap - r2.y * aq;
+                        Am[(size_t)i * ld + q] = r2.y * ap + r2.x * aq;
+                    }
+                }
             }
             __syncthreads();
             // rows: A[p, :], A[q, :]
-            for (int e = tid; e < half * ne; e += nt) {
-                const int k = e / ne, j = e - k * ne;
+            for (int k = wid; k < half; k += nwp) {
                 const int p = pq[k].x, q = pq[k].y;
                 const double2 r2 = cs[k];
-                const double ap = Am[(size_t)p * ld + j], aq = Am[(size_t)q * ld + j];
-                Am[(size_t)p * ld + j] = r2.x * ap - r2.y * aq;
-                Am[(size_t)q * ld + j] = r2.y * ap + r2.x * aq;
+                if (r2.y != 0.0) {
+                    for (int j = ln; j < ne; j += 32) {
+                        const double ap = Am[(size_t)p * ld + j], aq = Am[(size_t)q * ld + j];
+                        Am[(size_t)p * ld + j] = r2.x * ap - r2.y * aq;
+                        Am[(size_t)q * ld + j] = r2.y * ap + r2.x * aq;
+                    }
+                }
             }
             __syncthreads();
         }
@@ -125,17 +132,21 @@ __global__ void __launch_bounds__(256) jacobi_apply_kernel(const double2* __rest
     for (int j = threadIdx.x; j < ne; j += blockDim.x) row[j] = (j == b) ? 1.0 : 0.0;
     __syncthreads();
     const int R = *nrounds;
+    // thread k replays rotation k of every round; the (c, s) pair of the next round is fetched while the current
+    // one is applied (the log lives in L2, its latency would otherwise be paid once per round)
+    const int k = threadIdx.x;
+    double2 cur = (k < half && R > 0) ? rotlog[k] : make_double2(1.0, 0.0);
     for (int rd = 0; rd < R; ++rd) {
-        const int rr = rd % (ne - 1);
-        for (int k = threadIdx.x; k < half; k += blockDim.x) {
+        const double2 nxt = (k < half && rd + 1 < R) ? rotlog[(size_t)(rd + 1) * half + k] : make_double2(1.0, 0.0);
+        if (k < half && cur.y != 0.0) {
             int p, q;
-            rr_pair(ne, rr, k, p, q);
-            const double2 r2 = rotlog[(size_t)rd * half + k];
+            rr_pair(ne, rd % (ne - 1), k, p, q);
             const double vp = row[p], vq = row[q];
-            row[p] = r2.x * vp - r2.y * vq;
-            row[q] = r2.y * vp + r2.x * vq;
+            row[p] = cur.x * vp - cur.y * vq;
+            row[q] = cur.y * vp + cur.x * vq;
         }
         __syncthreads();
+        cur = nxt;
     }
     for (int j = threadIdx.x; j < n; j += blockDim.x) V[(size_t)b * n + j] = row[j];
 }
@@ -349,7 +360,11 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
     LQ_TRY(lam.alloc(c, sizeof(double) * n));
     LQ_TRY(Vraw.alloc(c, sizeof(double) * (size_t)n * n));
     const size_t smem = use_global ? (size_t)half * sizeof(double2) + 64 : need;
-    jacobi_kernel<<<1, 512, smem, c->stream>>>(G, n, Aw.as<double>(), use_global, rot.as<double2>(), max_sweeps,
+    // a pair is rotated while |a_pq| > rel_tol * sqrt(a_pp a_qq); 4 eps stops the tail of sweeps that only chase
+    // rounding noise (eigenvalues move by O(a_pq^2 / gap), the eigenvector basis stays a product of exact rotations)
+    double rel_tol = 4.0 * 1.1102230246251565e-16;
+    if (const char* env = getenv("LINALG_B200_JACOBI_TOL")) rel_tol = atof(env) * 1.1102230246251565e-16;
+    jacobi_kernel<<<1, 1024, smem, c->stream>>>(G, n, Aw.as<double>(), use_global, rot.as<double2>(), max_sweeps, rel_tol,
                                                nr.as<int>(), lam.as<double>());
     LQ_CHECK_LAUNCH(c);
     jacobi_apply_kernel<<<n, 128, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, Vraw.as<double>());

@@ -17,6 +17,13 @@ A = np.random.default_rng(3).standard_normal((20000, 32)) * np.logspace(0, -9, 3
 A[:, 5] = A[:, 4] * (1 + 1e-9) + 1e-9 * A[:, 6]
 Q, R = lb.tsqr(A, ctx=ctx)
 print("ill-cond: resid", orc.qr_residual(A, Q, R), "orth", orc.orth_error(Q), "diag>0", bool(np.all(np.diag(R) > 0)), flush=True)
+M0 = np.random.default_rng(9).standard_normal((4096, 128)); G0 = M0.T @ M0
+dG, dl, dV = ctx.upload(G0), ctx.alloc(8 * 128), ctx.alloc(8 * 128 * 128)
+ms = []
+for _ in range(4):
+    ctx.record(0); ctx.call("lq_eigh_dev", dG.ptr, 128, dl.ptr, dV.ptr); ctx.record(1); ms.append(ctx.elapsed_ms(0, 1))
+lam = ctx.download(dl, (128,)); ref = np.linalg.eigvalsh(G0)[::-1]
+print(f"eigh 128: {min(ms[1:]):.2f} ms, max rel err {np.max(np.abs(lam-ref)/ref):.2e}", flush=True)
 m, n = 1 << 20, 128
 A = np.random.default_rng(6).standard_normal((m, n))
 dA, dQ, dR = ctx.upload(A), ctx.alloc(A.nbytes), ctx.alloc(8 * n * n)
