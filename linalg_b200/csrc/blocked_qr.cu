@@ -365,16 +365,19 @@ struct EventPool {
 int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
-    cudaStream_t s_main = c->stream, s_side = c->lane[0];
+    cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1];
     const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
     DevBuf Tloc, G, W, W2, Ws, W2s;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+    DevBuf Wearly;  // split-K partials of V^T C_next, produced on the aux stream while the Gram matrix is formed
+    const size_t wearly_bytes = sizeof(double) * NB_OUT * NB_OUT * 160;
     if (lookahead) {
         LQ_TRY(Ws.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
         LQ_TRY(W2s.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+        LQ_TRY(Wearly.alloc(c, wearly_bytes));
     }
     double* Tall;
     if (keep) {
@@ -394,6 +397,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         LQ_TRY(pool.make(c, &e0));
         LQ_CUDA(c, cudaEventRecord(e0, s_main));
         LQ_CUDA(c, cudaStreamWaitEvent(s_side, e0, 0));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_aux, e0, 0));
     }
     for (int blk = 0; blk < nblocks; ++blk) {
         const int k0 = blk * NB_OUT;
@@ -417,6 +421,30 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
                                              W.as<double>(), W2.as<double>()));
         }
         const double* Vb = V + (size_t)k0 * ldv + k0;
+        // the product V^T C_next does not need the merged T: start it on the aux stream now, next to the Gram matrix
+        int early_splits = 0;
+        long long early_stride = 0;
+        cudaEvent_t ev_early = nullptr;
+        {
+            const int ntr0 = npad - (k0 + kb);
+            const int nnext0 = std::min(NB_OUT, ntr0);
+            if (lookahead && nnext0 > 0 && nin > 1) {
+                cudaEvent_t ev_v;
+                LQ_TRY(pool.make(c, &ev_v));
+                LQ_CUDA(c, cudaEventRecord(ev_v, s_main));
+                StreamScope aux(c, s_aux);
+                LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_v, 0));
+                if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_rest_prev, 0));
+                const int rc = vtc_partials(c, kb, nnext0, mk, Vb, ldv, A + (size_t)k0 * lda + k0 + kb, lda, Wearly.as<double>(),
+                                            wearly_bytes, &early_splits, &early_stride);
+                if (rc == LQ_OK) {
+                    LQ_TRY(pool.make(c, &ev_early));
+                    LQ_CUDA(c, cudaEventRecord(ev_early, s_aux));
+                } else if (rc != LQ_ERR_UNSUPPORTED && rc != LQ_ERR_NOMEM) {
+                    return rc;
+                }
+            }
+        }
         if (nin > 1) {
             int grc = LQ_ERR_UNSUPPORTED;
             if (kb == NB_OUT && getenv("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, kb, mk, Vb, ldv, Vb, ldv))
@@ -446,8 +474,15 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         LQ_CUDA(c, cudaEventRecord(ev_panel, s_main));
         if (nnext > 0) {
             if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
-            LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
-                                         W2.as<double>()));
+            if (ev_early) {
+                LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_early, 0));
+                LQ_TRY(vtc_finish(c, Wearly.as<double>(), early_splits, early_stride, kb, nnext, Tblk, NB_OUT, true,
+                                  W2.as<double>()));
+                LQ_TRY(gemm(c, false, false, mk, nnext, kb, -1.0, Vb, ldv, W2.as<double>(), nnext, 1.0, Ctr, lda));
+            } else {
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
+                                             W2.as<double>()));
+            }
         }
         if (nrest > 0 || (B && nrhs_pad > 0)) {
             StreamScope side(c, s_side);

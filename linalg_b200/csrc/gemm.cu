@@ -351,6 +351,9 @@ int launch_generic(Ctx* c, long long M, int N, int K, double alpha, const double
 // when `parts` is given, the split-K partial sums are left in a workspace for a fused consumer kernel
 struct Partials {
     DevBuf ws;
+    double* ext = nullptr;       // caller-owned workspace (used instead of `ws` when large enough)
+    size_t ext_bytes = 0;
+    double* ptr = nullptr;       // where the partial sums are
     int splits = 1;
     long long stride = 0;
 };
@@ -393,8 +396,15 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     if (splits == 1 && !parts) {
         g.C = C; g.ldc = ldc; g.split_stride = 0;
     } else {
-        LQ_TRY(ws.alloc(c, (size_t)splits * M * N * sizeof(double)));
-        g.C = ws.as<double>(); g.ldc = N; g.split_stride = M * (long long)N;
+        const size_t need = (size_t)splits * M * N * sizeof(double);
+        if (parts && parts->ext && parts->ext_bytes >= need) {
+            g.C = parts->ext;
+        } else {
+            LQ_TRY(ws.alloc(c, need));
+            g.C = ws.as<double>();
+        }
+        g.ldc = N; g.split_stride = M * (long long)N;
+        if (parts) parts->ptr = g.C;
         if (splits == 1) { g.alpha = 1.0; g.beta = 0.0; }  // raw product into the workspace
     }
     CUtensorMap mapA, mapB;
@@ -414,7 +424,7 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
     if (splits > 1) {
         const long long total = M * N;
         const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, c->stream>>>(ws.as<double>(), splits, g.split_stride, M, N, alpha, beta, C, ldc);
+        splitk_reduce_kernel<<<blocks, 256, 0, c->stream>>>(g.C, splits, g.split_stride, M, N, alpha, beta, C, ldc);
         LQ_CHECK_LAUNCH(c);
         LQ_COUNT_LAUNCH(c);
     }
@@ -534,6 +544,9 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
     return LQ_OK;
 }
 
+int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int kb, int nc, const double* T, int ldt,
+               bool trans_t, double* W2);
+
 // W2 (kb x nc, ld nc) = op(T) * (V^T C):  V (mk x kb, ldv), C (mk x nc, ldc), T (kb x kb upper, ldt), kb <= 128.
 // One split-K tensor-core GEMM whose partial sums feed a fused reduce + triangular-multiply kernel.
 int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
@@ -554,6 +567,11 @@ int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, c
     }
     Partials parts;
     LQ_TRY((launch_fast<true, false>(c, kb, nc, Kmain, 1.0, V, ldv, Cm, ldc, 0.0, nullptr, nc, &parts)));
+    return vtc_finish(c, parts.ptr, parts.splits, parts.stride, kb, nc, T, ldt, trans_t, W2);
+}
+
+int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int kb, int nc, const double* T, int ldt,
+               bool trans_t, double* W2) {
     const size_t rat_smem = ((size_t)kb * (kb + 1) + (size_t)kb * 33 + 8) * sizeof(double);
     static bool rat_configured[64] = {};
     if (!rat_configured[c->device]) {
@@ -561,10 +579,29 @@ int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, c
                                         (int)((128 * 129 + 128 * 33 + 8) * sizeof(double))));
         rat_configured[c->device] = true;
     }
-    reduce_apply_t_kernel<<<(nc + 31) / 32, 1024, rat_smem, c->stream>>>(parts.ws.as<double>(), parts.splits, parts.stride, kb,
-                                                                       nc, T, ldt, trans_t ? 1 : 0, W2);
+    reduce_apply_t_kernel<<<(nc + 31) / 32, 1024, rat_smem, c->stream>>>(partials, splits, stride, kb, nc, T, ldt,
+                                                                       trans_t ? 1 : 0, W2);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+// first half only: the split-K partial sums of V^T C into the caller's workspace (on the CURRENT stream of the
+// context); vtc_finish() later reduces them and applies op(T).  Returns LQ_ERR_UNSUPPORTED when the shape needs the
+// generic path (the caller then uses gemm_vtc_apply_t).
+int vtc_partials(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, double* ws,
+                 size_t ws_bytes, int* splits, long long* stride) {
+    const int Kmain = mk - mk % BK;
+    const bool fast = kb <= 128 && Kmain >= BK && Kmain == mk && aligned16(V) && aligned16(Cm) && (ldv % 2 == 0) &&
+                      (ldc % 2 == 0) && (kb % 4 == 0) && (nc % 2 == 0) && !getenv("LINALG_B200_NO_FAST_GEMM");
+    if (!fast) return LQ_ERR_UNSUPPORTED;
+    Partials parts;
+    parts.ext = ws;
+    parts.ext_bytes = ws_bytes;
+    LQ_TRY((launch_fast<true, false>(c, kb, nc, Kmain, 1.0, V, ldv, Cm, ldc, 0.0, nullptr, nc, &parts)));
+    if (parts.ptr != ws) return LQ_ERR_NOMEM;  // workspace too small: must not happen with the sizes used by the caller
+    *splits = parts.splits;
+    *stride = parts.stride;
     return LQ_OK;
 }
 

@@ -15,6 +15,12 @@ int gemm(Ctx* c, bool transa, bool transb, long long m, int n, int k, double alp
 int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
                      int ldt, bool trans_t, double* W2);
 
+// the same in two phases (partials on one stream, reduction + op(T) on another once T exists)
+int vtc_partials(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, double* ws,
+                 size_t ws_bytes, int* splits, long long* stride);
+int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int kb, int nc, const double* T, int ldt,
+               bool trans_t, double* W2);
+
 // ---- vtc_cluster.cu: the same product in one cluster launch (split-K over DSMEM); mode 0: no T, 1: T^T, 2: T
 bool vtc_cluster_supported(int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc);
 int vtc_cluster(Ctx* c, int mode, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
