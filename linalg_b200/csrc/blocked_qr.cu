@@ -94,18 +94,22 @@ __global__ void __launch_bounds__(128) larft_from_gram_kernel(const double* __re
 // the whole outer block, using the Gram matrix G = V^T V:  for column block b = 1 .. nblk-1
 //     T[0:R, b] = -T[0:R, 0:R] * G[0:R, b] * T[b, b],   R = 32 b
 // (the block form of LAPACK dlarft; V1 := the first R reflectors).  One CTA, everything in shared memory.
+template <int KBC>  // KBC = 128: compile-time block size (shifts instead of integer divisions); 0: runtime kb
 __global__ void __launch_bounds__(1024) merge_t_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T, int ldt,
-                                                      int kb) {
+                                                       int kb_rt) {
+    const int kb = KBC ? KBC : kb_rt;
     extern __shared__ double sh[];
     double* Ts = sh;               // [128][129]
     double* Xs = Ts + 128 * 129;   // [96][33]
     double* Ys = Xs + 96 * 33;     // [96][33]
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nblk = kb / 32;
-    for (int e = tid; e < kb * kb; e += nt) {
-        const int i = e / kb, k = e - i * kb;
-        const bool diag_block = (i / 32 == k / 32);
-        Ts[i * 129 + k] = (diag_block && k >= i) ? T[(long long)i * ldt + k] : 0.0;
+    // only the diagonal 32 x 32 blocks are read: 4 independent loads per thread
+    for (int e = tid; e < kb * kb; e += nt) Ts[(e / kb) * 129 + (e % kb)] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < nblk * 32 * 32; e += nt) {
+        const int b = e >> 10, i = (e >> 5) & 31, k = e & 31;
+        if (k >= i) Ts[(32 * b + i) * 129 + 32 * b + k] = T[(long long)(32 * b + i) * ldt + 32 * b + k];
     }
     __syncthreads();
     for (int b = 1; b < nblk; ++b) {
@@ -117,9 +121,14 @@ __global__ void __launch_bounds__(1024) merge_t_kernel(const double* __restrict_
         __syncthreads();
         for (int e = tid; e < R * 32; e += nt) {
             const int i = e >> 5, cc = e & 31;
-            double acc = 0.0;
-            for (int k = i; k < R; ++k) acc = fma(Ts[i * 129 + k], Xs[k * 33 + cc], acc);
-            Ys[i * 33 + cc] = acc;
+            double a0 = 0.0, a1 = 0.0;
+            int k = i;
+            for (; k + 2 <= R; k += 2) {
+                a0 = fma(Ts[i * 129 + k], Xs[k * 33 + cc], a0);
+                a1 = fma(Ts[i * 129 + k + 1], Xs[(k + 1) * 33 + cc], a1);
+            }
+            if (k < R) a0 = fma(Ts[i * 129 + k], Xs[k * 33 + cc], a0);
+            Ys[i * 33 + cc] = a0 + a1;
         }
         __syncthreads();
         for (int e = tid; e < R * 32; e += nt) {
@@ -452,7 +461,8 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             if (grc == LQ_ERR_UNSUPPORTED)
                 grc = gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT);
             LQ_TRY(grc);
-            merge_t_kernel<<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
+            if (kb == 128) merge_t_kernel<128><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
+            else merge_t_kernel<0><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
             LQ_CHECK_LAUNCH(c);
             LQ_COUNT_LAUNCH(c);
         }
@@ -508,7 +518,8 @@ int configure_once(Ctx* c) {
     if (done[c->device]) return LQ_OK;
     LQ_CUDA(c, cudaFuncSetAttribute(larft_from_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)((128 * 129 + 128) * sizeof(double))));
-    LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
+    LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
+    LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
     done[c->device] = true;
     return LQ_OK;
 }
