@@ -61,6 +61,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// C[i] += v without reading it back: one RED per element, no load round trip in the epilogue.  Every element of C
+// is touched by exactly one thread of one CTA, so the result is as deterministic as load-add-store.
+__device__ __forceinline__ void red_add(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 // element (r, k) of a swizzled K-major tile (r & 7 must be passed as r7)
 __device__ __forceinline__ int sw_idx(int r, int r7, int k) { return r * BK + ((((k >> 1) ^ r7) << 1) | (k & 1)); }
 
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
     // read-modify-write epilogue ahead: pull my part of the C tile into L2 while the main loop runs
-    if (g.splits == 1 && g.beta != 0.0) {
+    if (g.splits == 1 && g.beta != 0.0 && g.beta != 1.0) {
 #pragma unroll
         for (int im = 0; im < 4; ++im)
 #pragma unroll
@@ -230,6 +235,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int r = wm * 64 + im * 16 + gq + half * 8;
             if (r >= mvalid) continue;
             double* crow = Cb + (m0 + r) * (long long)g.ldc + n0;
+            if (beta == 1.0) {  // accumulate in place: fire-and-forget reductions
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + 2 * tq;
+                    if (c < nvalid) red_add(crow + c, alpha * acc[im][jn][half * 2 + 0]);
+                    if (c + 1 < nvalid) red_add(crow + c + 1, alpha * acc[im][jn][half * 2 + 1]);
+                }
+                continue;
+            }
             double cold[4][2];
             if (beta != 0.0) {
 #pragma unroll
@@ -505,6 +519,260 @@ __global__ void __launch_bounds__(1024) reduce_apply_t_kernel(const double* __re
 
 }  // namespace
 
+// ------------------------------------------------------------------ rank-K products (K <= 128) with one operand resident
+// C = alpha * A * B + beta * C  (NN) where the contraction is short (the 128 reflectors of a block update
+// C -= V W, or U = A (V S^-1), Q = A R^-1 on tall-skinny matrices).  With K = 128 a 128 x 128 output tile has only
+// 8 k-tiles, so the generic kernel spends a third of each CTA's life filling its pipeline and reading C.  Here a
+// persistent CTA keeps ONE operand tile resident in shared memory for its whole life and walks along the other
+// dimension: ASTAT = the A row tile (128 x K, eight swizzled TMA boxes) stays and the B / C column tiles stream
+// (block updates); !ASTAT = the B column tile (K x 128) stays and the A / C row tiles stream (tall-skinny).  The
+// producer warp runs ahead across tile boundaries, so the next tile's operands land during the current epilogue.
+constexpr int RK_KT_MAX = 8;  // K <= 128
+constexpr size_t RK_SMEM_ASTAT = (size_t)RK_KT_MAX * BM * BK * 8 + (size_t)STAGES * TILE_BYTES + 16 * sizeof(uint64_t) + 1024;
+constexpr size_t RK_SMEM_BSTAT = (size_t)RK_KT_MAX * TILE_BYTES + (size_t)STAGES * BM * BK * 8 + 16 * sizeof(uint64_t) + 1024;
+
+struct RankArgs {
+    const double* B;
+    double* C;
+    long long M;
+    int N, K;
+    int ldb, ldc;
+    double alpha, beta;
+};
+
+template <bool ASTAT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_rank_kernel(const RankArgs g, const __grid_constant__ CUtensorMap mapA) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    constexpr int ABOX = BM * BK;  // doubles per swizzled A box
+    // layout: [resident operand][streamed ring][barriers]
+    double* res = reinterpret_cast<double*>(smem_raw);
+    double* ring = res + (ASTAT ? RK_KT_MAX * ABOX : RK_KT_MAX * TILE_DOUBLES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (ASTAT ? STAGES * TILE_DOUBLES : STAGES * ABOX));
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* res_full = bars + 2 * STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KT = g.K / BK;
+    const long long tm = (g.M + BM - 1) / BM;
+    const int tn = (g.N + BN - 1) / BN;
+    // fixed tile index (resident operand) and walk (streamed operand)
+    const long long fix = ASTAT ? blockIdx.y : blockIdx.x;
+    const long long walk0 = ASTAT ? blockIdx.x : blockIdx.y;
+    const long long walk_step = ASTAT ? gridDim.x : gridDim.y;
+    const long long walk_n = ASTAT ? tn : tm;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        mbar_init(res_full, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ===================== producer =====================
+        if (ASTAT) {
+            const long long m0 = fix * BM;
+            if (lane == 0) {
+                mbar_expect_tx(res_full, (uint32_t)(KT * ABOX * 8));
+                for (int kt = 0; kt < KT; ++kt) tma_load_2d(res + kt * ABOX, &mapA, kt * BK, (int)m0, res_full);
+            }
+        } else {
+            const int n0 = (int)fix * BN;
+            const int nvalid = min(BN, g.N - n0);
+            if (lane == 0) mbar_expect_tx(res_full, (uint32_t)(KT * BK * nvalid * 8));
+            __syncwarp();
+            if (lane < BK)
+                for (int kt = 0; kt < KT; ++kt)
+                    bulk_g2s(res + kt * TILE_DOUBLES + lane * PM, g.B + (long long)(kt * BK + lane) * g.ldb + n0, nvalid * 8, res_full);
+        }
+        int it = 0;
+        for (long long w = walk0; w < walk_n; w += walk_step) {
+            for (int kt = 0; kt < KT; ++kt, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (ASTAT) {
+                    const int n0 = (int)w * BN;
+                    const int nvalid = min(BN, g.N - n0);
+                    if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(BK * nvalid * 8));
+                    __syncwarp();
+                    if (lane < BK)
+                        bulk_g2s(ring + s * TILE_DOUBLES + lane * PM, g.B + (long long)(kt * BK + lane) * g.ldb + n0, nvalid * 8,
+                                 &full[s]);
+                } else {
+                    if (lane == 0) {
+                        mbar_expect_tx(&full[s], (uint32_t)(ABOX * 8));
+                        tma_load_2d(ring + s * ABOX, &mapA, kt * BK, (int)(w * BM), &full[s]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int wm = warp >> 2, wn = warp & 3;
+    const int gq = lane >> 2, tq = lane & 3;
+    mbar_wait(res_full, 0);
+    int it = 0;
+    for (long long w = walk0; w < walk_n; w += walk_step) {
+        const long long m0 = (ASTAT ? fix : w) * BM;
+        const int n0 = (int)(ASTAT ? w : fix) * BN;
+        const int mvalid = (int)min((long long)BM, g.M - m0);
+        const int nvalid = min(BN, g.N - n0);
+        if (g.beta != 0.0 && g.beta != 1.0 && tq == 0) {
+            // pull my part of the C tile into L2 while the 8 k-tiles run
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const int r = wm * 64 + (h >> 1) * 16 + gq + (h & 1) * 8;
+                if (r < mvalid) {
+                    const double* crow = g.C + (m0 + r) * (long long)g.ldc + n0 + wn * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(crow));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16));
+                }
+            }
+        }
+        double acc[4][4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            const double* sA = ASTAT ? res + kt * ABOX : ring + s * ABOX;
+            const double* sB = ASTAT ? ring + s * TILE_DOUBLES : res + kt * TILE_DOUBLES;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                double bf[4][2];
+                const int kA = ks * 8 + tq;
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + gq;
+                    bf[jn][0] = sB[kA * PM + c];
+                    bf[jn][1] = sB[(kA + 4) * PM + c];
+                }
+#pragma unroll
+                for (int im = 0; im < 4; ++im) {
+                    double af[4];
+                    const int r = wm * 64 + im * 16 + gq;
+                    af[0] = sA[sw_idx(r, gq, kA)];
+                    af[1] = sA[sw_idx(r + 8, gq, kA)];
+                    af[2] = sA[sw_idx(r, gq, kA + 4)];
+                    af[3] = sA[sw_idx(r + 8, gq, kA + 4)];
+#pragma unroll
+                    for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af, bf[jn]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- epilogue of this tile
+        const bool vec2 = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll
+        for (int im = 0; im < 4; ++im) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = wm * 64 + im * 16 + gq + half * 8;
+                if (r >= mvalid) continue;
+                double* crow = g.C + (m0 + r) * (long long)g.ldc + n0;
+                if (g.beta == 1.0) {
+#pragma unroll
+                    for (int jn = 0; jn < 4; ++jn) {
+                        const int c = wn * 32 + jn * 8 + 2 * tq;
+                        if (c < nvalid) red_add(crow + c, g.alpha * acc[im][jn][half * 2 + 0]);
+                        if (c + 1 < nvalid) red_add(crow + c + 1, g.alpha * acc[im][jn][half * 2 + 1]);
+                    }
+                    continue;
+                }
+                double cold[4][2];
+                if (g.beta != 0.0) {
+#pragma unroll
+                    for (int jn = 0; jn < 4; ++jn) {
+                        const int c = wn * 32 + jn * 8 + 2 * tq;
+                        cold[jn][0] = 0.0;
+                        cold[jn][1] = 0.0;
+                        if (vec2 && c + 1 < nvalid) {
+                            const double2 t2 = *reinterpret_cast<const double2*>(crow + c);
+                            cold[jn][0] = t2.x;
+                            cold[jn][1] = t2.y;
+                        } else {
+                            if (c < nvalid) cold[jn][0] = crow[c];
+                            if (c + 1 < nvalid) cold[jn][1] = crow[c + 1];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + 2 * tq;
+                    double v0 = g.alpha * acc[im][jn][half * 2 + 0];
+                    double v1 = g.alpha * acc[im][jn][half * 2 + 1];
+                    if (g.beta != 0.0) {
+                        v0 = fma(g.beta, cold[jn][0], v0);
+                        v1 = fma(g.beta, cold[jn][1], v1);
+                    }
+                    if (vec2 && c + 1 < nvalid) {
+                        *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);
+                    } else {
+                        if (c < nvalid) crow[c] = v0;
+                        if (c + 1 < nvalid) crow[c + 1] = v1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// returns LQ_ERR_UNSUPPORTED when the shape is not a rank-K product this kernel takes
+int gemm_rank(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+              double* C, int ldc) {
+    if (getenv("LINALG_B200_NO_RANK_GEMM")) return LQ_ERR_UNSUPPORTED;
+    if (K > RK_KT_MAX * BK || K % BK != 0 || K < BK || (N % 2) != 0 || M < 2 * BM) return LQ_ERR_UNSUPPORTED;
+    const long long tm = (M + BM - 1) / BM;
+    const int tn = (N + BN - 1) / BN;
+    // which operand stays: the one whose tile is reused more often
+    const bool astat = tn >= 4;
+    if (!astat && tm < 4) return LQ_ERR_UNSUPPORTED;
+    // measured on B200: the B-stationary walk wins on tall-skinny products (30.2 vs 27.8 TFLOP/s at 2^20 x 128 x 128),
+    // the A-stationary walk does not beat the generic kernel on square block updates (23.6 vs 25.0) -> opt-in only
+    if (astat && !getenv("LINALG_B200_RANK_ASTAT")) return LQ_ERR_UNSUPPORTED;
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(gemm_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_SMEM_ASTAT));
+        LQ_CUDA(c, cudaFuncSetAttribute(gemm_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_SMEM_BSTAT));
+        configured[c->device] = true;
+    }
+    CUtensorMap mapA;
+    LQ_TRY(make_kmajor_map(c, &mapA, A, M, K, lda));
+    RankArgs g;
+    g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha; g.beta = beta;
+    const long long fixed_tiles = astat ? tm : tn;
+    const long long walk_tiles = astat ? tn : tm;
+    // CTAs per fixed tile: fill the SMs once (persistent), at most one CTA per walked tile
+    long long per_fixed = std::max<long long>(1, std::min<long long>(walk_tiles, (c->sm_count + fixed_tiles - 1) / fixed_tiles));
+    // prefer a whole number of equal walks
+    while (per_fixed > 1 && fixed_tiles * per_fixed > (long long)c->sm_count && fixed_tiles * (per_fixed - 1) >= c->sm_count * 3 / 4)
+        --per_fixed;
+    if (astat) {
+        dim3 grid((unsigned)per_fixed, (unsigned)tm);
+        gemm_rank_kernel<true><<<grid, GEMM_THREADS, RK_SMEM_ASTAT, c->stream>>>(g, mapA);
+    } else {
+        dim3 grid((unsigned)tn, (unsigned)per_fixed);
+        gemm_rank_kernel<false><<<grid, GEMM_THREADS, RK_SMEM_BSTAT, c->stream>>>(g, mapA);
+    }
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
 int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, const double* A, int lda, const double* B,
          int ldb, double beta, double* C, int ldc) {
     if (M <= 0 || N <= 0) return LQ_OK;
@@ -526,6 +794,10 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
         return launch_generic<false, false>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     }
     int rc;
+    if (!ta && !tb && Kmain == K) {
+        rc = gemm_rank(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    }
     if (ta && tb) rc = launch_fast<true, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (ta) rc = launch_fast<true, false>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (tb) rc = launch_fast<false, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
