@@ -87,16 +87,33 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const double* __restrict__
                 rotlog[(size_t)rounds * half + kk] = make_double2(cc, ss);
             }
             __syncthreads();
-            // columns: A[:, p], A[:, q] -- one warp per rotation pair, lanes over the rows (no integer division)
+            // columns: A[:, p], A[:, q] -- one warp per rotation pair, lanes over the rows; 32-bit indexing and a
+            // 4-way unrolled body (the solver is instruction bound on its single SM)
             const int wid = tid >> 5, ln = tid & 31, nwp = nt >> 5;
             for (int k = wid; k < half; k += nwp) {
                 const int p = pq[k].x, q = pq[k].y;
                 const double2 r2 = cs[k];
                 if (r2.y != 0.0) {
-                    for (int i = ln; i < ne; i += 32) {
-                        const double ap = Am[(size_t)i * ld + p], aq = Am[(size_t)i * ld + q];
-                        Am[(size_t)i * ld + p] = r2.x * ap - r2.y * aq;
-                        Am[(size_t)i * ld + q] = r2.y * ap + r2.x * aq;
+                    double* colp = Am + p;
+                    double* colq = Am + q;
+                    int i = ln;
+                    for (; i + 96 < ne; i += 128) {
+                        double ap[4], aq[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ap[u] = colp[(i + 32 * u) * ld];
+                            aq[u] = colq[(i + 32 * u) * ld];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            colp[(i + 32 * u) * ld] = r2.x * ap[u] - r2.y * aq[u];
+                            colq[(i + 32 * u) * ld] = r2.y * ap[u] + r2.x * aq[u];
+                        }
+                    }
+                    for (; i < ne; i += 32) {
+                        const double ap = colp[i * ld], aq = colq[i * ld];
+                        colp[i * ld] = r2.x * ap - r2.y * aq;
+                        colq[i * ld] = r2.y * ap + r2.x * aq;
                     }
                 }
             }
@@ -106,10 +123,26 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const double* __restrict__
                 const int p = pq[k].x, q = pq[k].y;
                 const double2 r2 = cs[k];
                 if (r2.y != 0.0) {
-                    for (int j = ln; j < ne; j += 32) {
-                        const double ap = Am[(size_t)p * ld + j], aq = Am[(size_t)q * ld + j];
-                        Am[(size_t)p * ld + j] = r2.x * ap - r2.y * aq;
-                        Am[(size_t)q * ld + j] = r2.y * ap + r2.x * aq;
+                    double* rowp = Am + p * ld;
+                    double* rowq = Am + q * ld;
+                    int j = ln;
+                    for (; j + 96 < ne; j += 128) {
+                        double ap[4], aq[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ap[u] = rowp[j + 32 * u];
+                            aq[u] = rowq[j + 32 * u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            rowp[j + 32 * u] = r2.x * ap[u] - r2.y * aq[u];
+                            rowq[j + 32 * u] = r2.y * ap[u] + r2.x * aq[u];
+                        }
+                    }
+                    for (; j < ne; j += 32) {
+                        const double ap = rowp[j], aq = rowq[j];
+                        rowp[j] = r2.x * ap - r2.y * aq;
+                        rowq[j] = r2.y * ap + r2.x * aq;
                     }
                 }
             }
