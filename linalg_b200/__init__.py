@@ -22,6 +22,7 @@ from .qr import (
     tsqr,
 )
 from .svd import svd
+from .extras import pca, project_onto_colspace
 from .utils import EPS, shard_bounds
 
 __all__ = [
@@ -41,6 +42,8 @@ __all__ = [
     "default_context",
     "pinned_empty",
     "shard_bounds",
+    "project_onto_colspace",
+    "pca",
 ]
 
 __version__ = "0.1.0"

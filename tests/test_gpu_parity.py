@@ -391,6 +391,43 @@ def test_tsqr_ill_conditioned_falls_back_to_householder(ctx):
     assert orc.qr_residual(A, Q, R) <= RESID and orc.orth_error(Q) <= ORTH
 
 
+# ------------------------------------------------------------------ section 8(f) "next" rows: callers of the path
+def test_project_onto_colspace(ctx):
+    # the reference's hand-computed case, tests/test_projections.py:12-44
+    A = np.array([[1, 0], [1, 1], [1, 2]])
+    b = np.array([[6], [0], [0]])
+    p = lb.project_onto_colspace(A, b, ctx=ctx)
+    np.testing.assert_allclose(p, np.array([[5], [2], [-1]]), atol=1e-12)
+    res = np.linalg.norm(A @ np.linalg.lstsq(A, b, rcond=None)[0] - b, np.inf)
+    assert abs(res - np.linalg.norm(p - b, np.inf)) < 1e-12
+    # random tall matrix, several right-hand sides, and a rank-deficient one (pseudo-inverse branch upstream)
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((300, 40)); B = rng.standard_normal((300, 5))
+    P = lb.project_onto_colspace(A, B, ctx=ctx)
+    assert orc.rel_max_err(P, A @ np.linalg.lstsq(A, B, rcond=None)[0]) <= 1e-10
+    A[:, 7] = A[:, 3] + A[:, 4]
+    P = lb.project_onto_colspace(A, B[:, 0], ctx=ctx)
+    assert P.shape == (300, 1)
+    assert orc.rel_max_err(P, A @ (np.linalg.pinv(A) @ B[:, :1])) <= 1e-9
+
+
+def test_pca_matches_numpy(ctx):
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((500, 12)) @ np.diag(np.linspace(3.0, 0.5, 12)) + 4.0
+    k = 5
+    pcs, scores, ev, evr, tv, mean_ = lb.pca(A, k, ctx=ctx)
+    X = A - A.mean(axis=0)
+    _, S, Vt = np.linalg.svd(X, full_matrices=False)
+    np.testing.assert_allclose(ev, S[:k] ** 2 / 499, rtol=1e-10)
+    np.testing.assert_allclose(tv, np.linalg.norm(X) ** 2 / 499, rtol=1e-12)
+    np.testing.assert_allclose(evr, ev / tv, rtol=1e-12)
+    np.testing.assert_allclose(mean_, A.mean(axis=0), rtol=1e-14)
+    sg = np.sign(np.sum(pcs * Vt[:k].T, axis=0))
+    assert orc.rel_max_err(pcs * sg, Vt[:k].T) <= 1e-8
+    assert orc.rel_max_err(scores * sg, X @ Vt[:k].T) <= 1e-8
+    assert np.abs(pcs.T @ pcs - np.eye(k)).max() <= 1e-10
+
+
 def test_no_cpu_fallback_loaded(ctx):
     """The numbers above came from the in-tree CUDA library: it is the loaded object and it counted launches."""
     from linalg_b200 import _native
