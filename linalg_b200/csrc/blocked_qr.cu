@@ -60,36 +60,6 @@ __global__ void __launch_bounds__(256) set_identity_kernel(double* __restrict__ 
     }
 }
 
-// T (kb x kb upper, row-major ldt) from the Gram matrix G = V^T V of unit-norm reflectors:
-//   tau_j = 2 (0 for a skipped, i.e. zero, reflector);  T[j][j] = tau_j;
-//   T[0:j, j] = -tau_j * T[0:j, 0:j] * G[0:j, j]                          (LAPACK dlarft, forward/columnwise)
-__global__ void __launch_bounds__(128) larft_from_gram_kernel(const double* __restrict__ G, int ldg, double* __restrict__ T,
-                                                              int ldt, int kb) {
-    extern __shared__ double sh[];
-    double* Ts = sh;                      // Ts[k * 129 + i] = T[i][k]
-    double* gcol = sh + 128 * 129;        // 128
-    const int i = threadIdx.x;
-    for (int e = i; e < 128 * 129; e += blockDim.x) Ts[e] = 0.0;
-    __syncthreads();
-    for (int j = 0; j < kb; ++j) {
-        if (i < kb) gcol[i] = G[(long long)i * ldg + j];
-        __syncthreads();
-        const double tau = (gcol[j] > 0.5) ? 2.0 : 0.0;
-        double acc = 0.0;
-        if (i < j) {
-            for (int k = i; k < j; ++k) acc = fma(Ts[k * 129 + i], gcol[k], acc);
-        }
-        __syncthreads();
-        if (i < j) Ts[j * 129 + i] = -tau * acc;
-        if (i == j) Ts[j * 129 + i] = tau;
-        __syncthreads();
-    }
-    for (int e = i; e < kb * kb; e += blockDim.x) {
-        const int r = e / kb, c = e - r * kb;
-        T[(long long)r * ldt + c] = Ts[c * 129 + r];
-    }
-}
-
 // Merge the 32 x 32 panel factors on the diagonal of T (kb x kb, kb = 32 * nblk <= 128) into the factor of
 // the whole outer block, using the Gram matrix G = V^T V:  for column block b = 1 .. nblk-1
 //     T[0:R, b] = -T[0:R, 0:R] * G[0:R, b] * T[b, b],   R = 32 b
@@ -516,8 +486,6 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
 int configure_once(Ctx* c) {
     static bool done[64] = {};
     if (done[c->device]) return LQ_OK;
-    LQ_CUDA(c, cudaFuncSetAttribute(larft_from_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)((128 * 129 + 128) * sizeof(double))));
     LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
     LQ_CUDA(c, cudaFuncSetAttribute(merge_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MERGE_T_SMEM));
     done[c->device] = true;
