@@ -121,19 +121,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
             for (int s = so; s < C; ++s) {
                 d[s] = fma(vv.x, r[s][ii], d[s]);
-                d2[s] = fma(vv.y, r[s][ii + 1], d2[s]);
+                if (C - so >= 3) d[s] = fma(vv.y, r[s][ii + 1], d[s]);   // >= 3 independent chains already
+                else d2[s] = fma(vv.y, r[s][ii + 1], d2[s]);
             }
         }
+        if (C - so < 3) {
 #pragma unroll
-        for (int s = so; s < C; ++s) d[s] += d2[s];
+            for (int s = so; s < C; ++s) d[s] += d2[s];
+        }
         // sum of squares of x = the owner column's own dot product
         double ss = group_sum<P, C>(d[so]);
         ss = __shfl_sync(0xffffffffu, ss, lo, L);
         const double x0 = vb[j * D::ROWP + jp * D::PSTRIDE + iib];
 
-        double rinv;
         const double ssc = fmax(ss, 1e-300);
-        const double nrm = sqrt_nr_t<NR>(ssc, rinv);
+        // ||x|| = ss * rsqrt(ss): the Newton-refined rsqrt is good to 2.7e-16 (lq_probe 13), so the extra
+        // correction step of sqrt_nr_t would only polish the last bit of R[j][j] while sitting on the serial chain
+        const double nrm = ssc * rsqrt_nr_t<NR>(ssc);
         const bool skip = nrm < kEps;  // qr.py:79-80
         const double alpha = copysign(nrm, x0);
         const double v0 = x0 + alpha;
@@ -223,11 +227,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
             for (int s = so; s < C; ++s) {
                 d[s] = fma(vv.x, q[s][ii], d[s]);
-                d2[s] = fma(vv.y, q[s][ii + 1], d2[s]);
+                if (C - so >= 3) d[s] = fma(vv.y, q[s][ii + 1], d[s]);
+                else d2[s] = fma(vv.y, q[s][ii + 1], d2[s]);
             }
         }
+        if (C - so < 3) {
 #pragma unroll
-        for (int s = so; s < C; ++s) d[s] += d2[s];
+            for (int s = so; s < C; ++s) d[s] += d2[s];
+        }
 #pragma unroll
         for (int s = so; s < C; ++s) d[s] = beta * group_sum<P, C>(d[s]);
 #pragma unroll
