@@ -124,6 +124,11 @@ int lq_svd_gram_sharded_dev(lq_ctx* ctx, const double* A_local, int64_t m_local,
  * 2: device copy [GB/s]; 4: dependent DFMA latency [cycles]; 10..16: accuracy of the MUFU seeds and
  * Newton-refined rcp / rsqrt / sqrt used by the kernels [max relative error]. */
 int lq_probe(lq_ctx* ctx, int kind, double* result);
+/* diagnostics: one 32-column panel factorisation of the blocked path with an explicit kernel version
+ * (0 default, 1 barrier.cluster kernel, 2 / 3 st.async kernels with 512 / 256 rows per CTA) */
+int lq_debug_panel(lq_ctx* ctx, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb, int version);
+/* the same with clock64() stamps of the column-step phases: trace[2 warps][32 columns][8 phases] (device pointer) */
+int lq_debug_panel_trace(lq_ctx* ctx, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, long long* trace);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     "lq_svd_gram_sharded_dev": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_double, _DP, _DP, _DP,
                                           C.POINTER(C.c_int)]),
     "lq_probe": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_double)]),
+    "lq_debug_panel_trace": (C.c_int, [_CTX, _DP, C.c_int, _DP, C.c_int, _DP, C.c_int, C.c_int, C.c_void_p]),
+    "lq_debug_panel": (C.c_int, [_CTX, _DP, C.c_int, _DP, C.c_int, _DP, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@
 #include "../../include/linalg_b200.h"
 #include "ops.cuh"
 #include "panel.cuh"
+#include "panel2.cuh"
 
 namespace lq {
 
@@ -269,16 +270,11 @@ int detect_max_cluster(Ctx* c) {
     return best;
 }
 
-int panel_factor(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb) {
-    using Cfg = PanelCfg<4, 16>;
-    const int maxcs = detect_max_cluster(c);
-    int cs = 1;
-    while (cs * Cfg::ROWS_PER_CTA < mp && cs < maxcs) cs *= 2;
-    if (cs * Cfg::ROWS_PER_CTA < mp || nb > Cfg::NBMAX) return panel_generic(c, A, lda, V, ldv, T, ldt, mp, nb);
-    auto kern = panel_cluster_kernel<4, 16>;
+template <typename Kern, typename... Args>
+int launch_cluster(Ctx* c, Kern kern, int cs, int threads, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs);
-    cfg.blockDim = dim3(PANEL_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
@@ -288,9 +284,49 @@ int panel_factor(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    LQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, A, lda, V, ldv, T, ldt, mp, nb));
+    LQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, args...));
     LQ_COUNT_LAUNCH(c);
     return LQ_OK;
+}
+
+// version: 0 = default choice, 1 = barrier.cluster kernel (panel.cuh), 2 = st.async kernel (panel2.cuh), 16 rows per lane,
+// 3 = st.async kernel with 8 rows per lane (256 rows per CTA)
+int panel_factor_v(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb, int version) {
+    using Cfg = PanelCfg<4, 16>;
+    const int maxcs = detect_max_cluster(c);
+    if (version == 0) {
+        static const int env_version = getenv("LINALG_B200_PANEL") ? atoi(getenv("LINALG_B200_PANEL")) : 0;
+        version = env_version;
+    }
+    if (nb == P2_NB && version != 1) {
+        static bool attr_done[64] = {};
+        if (!attr_done[c->device]) {
+            cudaFuncSetAttribute(panel2_cluster_kernel<16, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(panel2_cluster_kernel<8, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            attr_done[c->device] = true;
+        }
+        // default: the 256-rows-per-CTA kernel whenever the panel fits a cluster of it (half the FP64 work per SM and
+        // column); taller panels run next to the side stream's big GEMMs, where the barrier.cluster kernel measured
+        // better in situ (tools/blocked_trace.py), although the 512-row st.async kernel wins stand-alone
+        if (version != 2 && mp <= maxcs * Panel2Cfg<8>::ROWS_PER_CTA) {
+            int cs = 1;
+            while (cs * Panel2Cfg<8>::ROWS_PER_CTA < mp) cs *= 2;
+            return launch_cluster(c, panel2_cluster_kernel<8, false>, cs, P2_THREADS, A, lda, V, ldv, T, ldt, mp, (long long*)nullptr);
+        }
+        if (version == 2 && mp <= maxcs * Panel2Cfg<16>::ROWS_PER_CTA) {
+            int cs = 1;
+            while (cs * Panel2Cfg<16>::ROWS_PER_CTA < mp) cs *= 2;
+            return launch_cluster(c, panel2_cluster_kernel<16, false>, cs, P2_THREADS, A, lda, V, ldv, T, ldt, mp, (long long*)nullptr);
+        }
+    }
+    int cs = 1;
+    while (cs * Cfg::ROWS_PER_CTA < mp && cs < maxcs) cs *= 2;
+    if (cs * Cfg::ROWS_PER_CTA < mp || nb > Cfg::NBMAX) return panel_generic(c, A, lda, V, ldv, T, ldt, mp, nb);
+    return launch_cluster(c, panel_cluster_kernel<4, 16>, cs, PANEL_THREADS, A, lda, V, ldv, T, ldt, mp, nb);
+}
+
+int panel_factor(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb) {
+    return panel_factor_v(c, A, lda, V, ldv, T, ldt, mp, nb, 0);
 }
 
 inline int grid_for(Ctx* c, long long total) {
@@ -325,8 +361,9 @@ struct EventPool {
     ~EventPool() {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
     }
+    bool timing = false;
     int make(Ctx* c, cudaEvent_t* out) {
-        LQ_CUDA(c, cudaEventCreateWithFlags(out, cudaEventDisableTiming));
+        LQ_CUDA(c, cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming));
         ev.push_back(*out);
         return LQ_OK;
     }
@@ -369,7 +406,18 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     }
     LQ_CUDA(c, cudaMemsetAsync(Tall, 0, sizeof(double) * NB_OUT * NB_OUT * (size_t)nblocks, s_main));
     EventPool pool;
+    // diagnostics (LINALG_B200_TRACE_BLOCKS=1): per outer block, when the panel chain, the next-block update and the
+    // side stream's trailing update finished (ms since the start of the factorisation), printed to stderr
+    const bool trace_blocks = lookahead && getenv("LINALG_B200_TRACE_BLOCKS") != nullptr;
+    pool.timing = trace_blocks;
+    struct BlockTrace { cudaEvent_t panels = nullptr, chain = nullptr, next = nullptr, rest = nullptr; };
+    std::vector<BlockTrace> btrace(trace_blocks ? nblocks : 0);
+    cudaEvent_t ev_t0 = nullptr;
     cudaEvent_t ev_rest_prev = nullptr;  // completion of the side stream's last trailing update
+    if (trace_blocks) {
+        LQ_TRY(pool.make(c, &ev_t0));
+        LQ_CUDA(c, cudaEventRecord(ev_t0, s_main));
+    }
     if (lookahead) {
         // the scratch buffers of the side stream come from the main stream's pool allocation
         cudaEvent_t e0;
@@ -398,6 +446,10 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             if (nrem > 0)
                 LQ_TRY(apply_block_reflector(c, Vp, ldv, Tp, ldtp, true, mp, NB_IN, Ap + NB_IN, lda, nrem,
                                              W.as<double>(), W2.as<double>()));
+        }
+        if (trace_blocks) {
+            LQ_TRY(pool.make(c, &btrace[blk].panels));
+            LQ_CUDA(c, cudaEventRecord(btrace[blk].panels, s_main));
         }
         const double* Vb = V + (size_t)k0 * ldv + k0;
         // the product V^T C_next does not need the merged T: start it on the aux stream now, next to the Gram matrix
@@ -452,6 +504,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         cudaEvent_t ev_panel;
         LQ_TRY(pool.make(c, &ev_panel));
         LQ_CUDA(c, cudaEventRecord(ev_panel, s_main));
+        if (trace_blocks) btrace[blk].chain = ev_panel;
         if (nnext > 0) {
             if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
             if (ev_early) {
@@ -463,6 +516,10 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
                                              W2.as<double>()));
             }
+        }
+        if (trace_blocks) {
+            LQ_TRY(pool.make(c, &btrace[blk].next));
+            LQ_CUDA(c, cudaEventRecord(btrace[blk].next, s_main));
         }
         if (nrest > 0 || (B && nrhs_pad > 0)) {
             StreamScope side(c, s_side);
@@ -477,9 +534,21 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             LQ_TRY(pool.make(c, &ev_rest));
             LQ_CUDA(c, cudaEventRecord(ev_rest, s_side));
             ev_rest_prev = ev_rest;
+            if (trace_blocks) btrace[blk].rest = ev_rest;
         }
     }
     if (lookahead && ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));  // join
+    if (trace_blocks) {
+        LQ_CUDA(c, cudaStreamSynchronize(s_main));
+        fprintf(stderr, "# blk  panels_done  chain_done  next_done  rest_done   (ms since start; m=%d npad=%d)\n", m, npad);
+        for (int blk = 0; blk < nblocks; ++blk) {
+            float t[4] = {-1.f, -1.f, -1.f, -1.f};
+            cudaEvent_t evs[4] = {btrace[blk].panels, btrace[blk].chain, btrace[blk].next, btrace[blk].rest};
+            for (int k = 0; k < 4; ++k)
+                if (evs[k]) cudaEventElapsedTime(&t[k], ev_t0, evs[k]);
+            fprintf(stderr, "%4d %10.3f %10.3f %10.3f %10.3f\n", blk, t[0], t[1], t[2], t[3]);
+        }
+    }
     return LQ_OK;
 }
 
@@ -658,6 +727,27 @@ int large_lstsq_householder(Ctx* c, const double* A, const double* B, int m, int
 using namespace lq;
 
 extern "C" {
+
+// diagnostics: one panel factorisation (mp x nb at A, lda) with an explicit kernel version (see panel_factor_v)
+int lq_debug_panel(lq_ctx* h, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb, int version) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return panel_factor_v(c, A, lda, V, ldv, T, ldt, mp, nb, version);
+}
+
+// diagnostics: the 256-rows-per-CTA st.async panel kernel with clock64() stamps (2 warps x 32 columns x 8 phases)
+int lq_debug_panel_trace(lq_ctx* h, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, long long* trace) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    const int maxcs = detect_max_cluster(c);
+    LQ_REQUIRE(c, mp <= maxcs * Panel2Cfg<8>::ROWS_PER_CTA, LQ_ERR_SHAPE, "panel too tall for the traced kernel");
+    cudaFuncSetAttribute(panel2_cluster_kernel<8, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    int cs = 1;
+    while (cs * Panel2Cfg<8>::ROWS_PER_CTA < mp) cs *= 2;
+    return launch_cluster(c, panel2_cluster_kernel<8, true>, cs, P2_THREADS, A, lda, V, ldv, T, ldt, mp, trace);
+}
 
 int lq_householder_qr_dev(lq_ctx* h, const double* A, int m, int n, double* Q, double* R) {
     Ctx* c = as_ctx(h);

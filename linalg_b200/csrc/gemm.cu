@@ -66,6 +66,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void red_add(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// the same for a whole row segment: the TMA engine reads the values from shared memory and adds them into global
+// memory (SASS UBLKRED.G.S.ADD.F64); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_red_add_f64(double* gmem_dst, const double* smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr int EPI_PITCH = 136;  // doubles per staged C row: 128 + 8 (a quarter-warp's 16-byte stores hit distinct banks)
+static_assert((size_t)BM * EPI_PITCH * 8 <= (size_t)STAGES * 2 * TILE_BYTES, "the staged C tile reuses the operand ring");
 // element (r, k) of a swizzled K-major tile (r & 7 must be passed as r7)
 __device__ __forceinline__ int sw_idx(int r, int r7, int k) { return r * BK + ((((k >> 1) ^ r7) << 1) | (k & 1)); }
 
@@ -228,6 +238,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const double alpha = direct ? g.alpha : 1.0;
     const double beta = direct ? g.beta : 0.0;
     const bool vec2 = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+    if (beta == 1.0 && vec2 && (nvalid & 1) == 0) {
+        // In-place accumulation through the TMA engine: the tile is staged in the (now idle) operand ring and leaves
+        // as one bulk reduce-add per row, so the 64 scalar REDs per thread disappear from the SM's issue slots and
+        // the CTA retires as soon as the engine has read the staging buffer.  One writer per element -> deterministic.
+        consumer_bar_sync();  // every consumer warp is done reading the operand stages
+        double* stg = tiles;
+#pragma unroll
+        for (int im = 0; im < 4; ++im)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = wm * 64 + im * 16 + gq + half * 8;
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int c = wn * 32 + jn * 8 + 2 * tq;
+                    *reinterpret_cast<double2*>(stg + r * EPI_PITCH + c) =
+                        make_double2(alpha * acc[im][jn][half * 2 + 0], alpha * acc[im][jn][half * 2 + 1]);
+                }
+            }
+        fence_proxy_async();
+        consumer_bar_sync();
+        if (lane < 16) {
+            const int r = warp * 16 + lane;
+            if (r < mvalid) bulk_red_add_f64(Cb + (m0 + r) * (long long)g.ldc + n0, stg + r * EPI_PITCH, (uint32_t)nvalid * 8u);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+        return;
+    }
 #pragma unroll
     for (int im = 0; im < 4; ++im) {
 #pragma unroll
