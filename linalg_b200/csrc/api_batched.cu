@@ -3,6 +3,7 @@
 
 #include "../../include/linalg_b200.h"
 #include "batched_qr32.cuh"
+#include "batched_qr32_pipe.cuh"
 #include "batched_small.cuh"
 #include "ctx.cuh"
 #include "ops.cuh"
@@ -22,6 +23,24 @@ static int launch_hh32(Ctx* c, cudaStream_t st, const double* A, long long batch
     }
     const long long per_block = (long long)WARPS * D::MPW;
     const long long blocks = (batch + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+// software-pipelined kernel (R phase of pair n+1 interleaved with the Q phase of pair n), persistent grid
+template <int WARPS, int MINB, int NR>
+static int launch_hh32_pipe(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
+    auto kern = hh_qr32_pipe_kernel<WARPS, MINB, NR>;
+    const size_t smem = (size_t)WARPS * Pipe32::WARP_DOUBLES * sizeof(double);
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device] = true;
+    }
+    const long long pairs = (batch + 1) / 2;
+    const long long blocks = std::min<long long>((long long)c->sm_count * MINB, (pairs + WARPS - 1) / WARPS);
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
@@ -60,6 +79,7 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 10: return launch_hh32<4, 4, 4, false, 5>(c, st, A, batch, Q, R);
             case 11: return launch_hh32<2, 2, 4, true, 3>(c, st, A, batch, Q, R);
             case 12: return launch_hh32<4, 4, 2, true, 8, 2>(c, st, A, batch, Q, R);
+            case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
             default: break;
         }
         set_error(c, "householder_qr_batched: unknown kernel variant %d", variant);

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         for (int s = 0; s < C; ++s) r[s][ii] = (row < mp) ? A[(long long)row * lda + colv[s]] : 0.0;
     }
     for (int e = threadIdx.x; e < 32 * 33; e += P2_THREADS) (&sm.Tt[0][0])[e] = 0.0;
+    for (int e = threadIdx.x; e < 2 * P2_MAXCS * 32; e += P2_THREADS) (&sm.recv[0][0][0])[e] = 0.0;
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
@@ -224,30 +225,48 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         mbar_wait(&sm.bar[par], (uint32_t)((j >> 1) & 1));
         P2_STAMP(5);
 
+        // totals: lane c holds column c.  Always 16 slots (the unused ones stay zero): no loop, no branches
         double tot;
         {
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;  // CS is 1, 2, 4, 8 or 16
-            if (CS >= 4) {
-                for (int t = 0; t < CS; t += 4) {
-                    t0 += sm.recv[par][t][lane];
-                    t1 += sm.recv[par][t + 1][lane];
-                    t2 += sm.recv[par][t + 2][lane];
-                    t3 += sm.recv[par][t + 3][lane];
-                }
-            } else {
-                for (int t = 0; t < CS; ++t) t0 += sm.recv[par][t][lane];
-            }
-            tot = (t0 + t1) + (t2 + t3);
+            double tt[P2_MAXCS];
+#pragma unroll
+            for (int t = 0; t < P2_MAXCS; ++t) tt[t] = sm.recv[par][t][lane];
+#pragma unroll
+            for (int o = P2_MAXCS / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int t = 0; t < o; ++t) tt[t] += tt[t + o];
+            tot = tt[0];
         }
         const double prow = sm.precv[par][lane];
+        const double x0 = sm.precv[par][j];                   // pivot (broadcast load)
         const double ss = __shfl_sync(0xffffffffu, tot, j);   // sum_{r>=j} x_r^2
-        const double x0 = __shfl_sync(0xffffffffu, prow, j);  // pivot
-        double rinv_n;
-        const double nrm = sqrt_nr_t<2>(fmax(ss, 1e-300), rinv_n);
+        // y = 1/||x||;  beta = 2 / v^T v = 1 / (||x|| (||x|| + |x0|)) = y^2 / (1 + |x0| y).  The reciprocal's seed comes
+        // from the unrefined y, so its MUFU runs beside the Newton steps of y instead of behind them.
+        const double ssc = fmax(ss, 1e-300);
+        const double ax0 = fabs(x0);
+        double y = rsqrt_seed(ssc);
+        double u = rcp_seed(fma(ax0, y, 1.0));
+        {
+            const double hx = 0.5 * ssc;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const double e = fma(-hx * y, y, 0.5);
+                y = fma(y, e, y);
+            }
+        }
+        const double nrm = ssc * y;
+        {
+            const double D = fma(ax0, y, 1.0);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const double e = fma(-D, u, 1.0);
+                u = fma(u, e, u);
+            }
+        }
         const bool skip = nrm < kEps;  // qr.py:79-80
         const double alpha = copysign(nrm, x0);
         const double v0 = x0 + alpha;
-        const double beta = skip ? 0.0 : rcp_nr_t<2>(nrm * fabs(v0));
+        const double beta = skip ? 0.0 : (y * y) * u;
         // g_c = v^T P[:, c] = x^T P[:, c] + alpha * P[j][c]
         const double gl = fma(alpha, prow, tot);
         double sc[C];

@@ -156,11 +156,272 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const double* __restrict__
     for (int i = tid; i < n; i += nt) lambda[i] = Am[(size_t)i * ld + i];
 }
 
+
+// One-sided (Hestenes) Jacobi for n <= 128: the columns of B = G J_1 J_2 ... are rotated until they are mutually
+// orthogonal, then B = V diag(lambda).  Why it is faster than jacobi_kernel: a round of the two-sided kernel reads and
+// writes the whole matrix twice (rows and columns: 98 k doubles of shared-memory traffic at n = 128, the 128 B/clk
+// port is the limit) behind three block barriers; here a round touches every column once and the three inner
+// products of a pair stay in registers.  Eight lanes own a column pair (16-byte loads, two rows per lane, 16-row
+// stride), four pairs per warp, Newton-refined MUFU reciprocals / rsqrt instead of the IEEE subroutines.
+//
+// Ordering (block round-robin): the ne / 4 blocks of four columns play a round-robin tournament; in a super-round a
+// warp owns one block pair (X, Y) and works through its 4 x 4 cross pairs in four steps that need only __syncwarp
+// (group g keeps column x_g in registers and meets y_{(g + t) mod 4} in step t), so the block barrier comes once per
+// FOUR rounds and the warps drift apart inside a super-round: loads, FP64 and the scalar chains of different warps
+// overlap instead of marching in lock step.  The six pairs inside each block are done in three steps at the start of
+// a sweep.  One sweep = 3 + 4 (ne / 4 - 1) steps of ne / 2 disjoint pairs = every pair once.  The (c, s) log is
+// indexed [step][slot = 4 warp + group] (64 slots per step); jacobi1s_pair() maps it back to the columns for the eigenvector replay.
+// ne = n padded to a multiple of 16 (zero columns never rotate).  B is left in Bout (column-major, pitch ne).
+__host__ __device__ inline int jacobi1s_steps_per_sweep(int ne) { return 3 + 4 * (ne / 4 - 1); }
+__device__ __forceinline__ bool jacobi1s_pair(int ne, int step, int slot, int& p, int& q) {
+    const int nblk = ne >> 2, w = slot >> 2, g = slot & 3;
+    if (step < 3) {
+        const int b = w + 16 * (g >> 1);  // two blocks per warp
+        if (b >= nblk) return false;
+        const int gg = g & 1;
+        // step 0: (0,1) (2,3); step 1: (0,2) (1,3); step 2: (0,3) (1,2)
+        const int lo = (gg == 0) ? 0 : (step == 0 ? 2 : 1);
+        const int hi = (gg == 0) ? (step + 1) : (step == 0 ? 3 : (step == 1 ? 3 : 2));
+        p = 4 * b + lo;
+        q = 4 * b + hi;
+        return true;
+    }
+    if (w >= (nblk >> 1)) return false;
+    const int sr = (step - 3) >> 2, t = (step - 3) & 3;
+    int X, Y;
+    rr_pair(nblk, sr, w, X, Y);
+    p = 4 * X + g;
+    q = 4 * Y + ((g + t) & 3);
+    return true;
+}
+
+// one rotation of the column pair held by an 8-lane group: ap / aq are the group's rows of columns p and q
+template <int NUMAX>
+__device__ __forceinline__ void jacobi1s_rotate(double (&ap)[2 * NUMAX], double (&aq)[2 * NUMAX], int NU, bool active, double floor_abs,
+                                                double rel_tol, double& cc, double& ss) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, g0 = 0.0, g1 = 0.0;
+#pragma unroll
+    for (int u = 0; u < NUMAX; ++u) {
+        if (u < NU) {
+            a0 = fma(ap[2 * u], ap[2 * u], a0), a1 = fma(ap[2 * u + 1], ap[2 * u + 1], a1);
+            b0 = fma(aq[2 * u], aq[2 * u], b0), b1 = fma(aq[2 * u + 1], aq[2 * u + 1], b1);
+            g0 = fma(ap[2 * u], aq[2 * u], g0), g1 = fma(ap[2 * u + 1], aq[2 * u + 1], g1);
+        }
+    }
+    double alpha = a0 + a1, beta = b0 + b1, gamma = g0 + g1;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+        beta += __shfl_xor_sync(0xffffffffu, beta, o);
+        gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+    }
+    cc = 1.0;
+    ss = 0.0;
+    // rotate while |p.q| > rel_tol ||p|| ||q||   (squared: gamma^2 > rel_tol^2 alpha beta)
+    if (active && fabs(gamma) > floor_abs && gamma * gamma > rel_tol * rel_tol * (alpha * beta)) {
+        // zeta = (beta - alpha) / (2 gamma), t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), c = 1 / sqrt(1 + t^2)
+        double zeta = (beta - alpha) * (0.5 * rcp_nr_t<2>(gamma));
+        zeta = fmin(fmax(zeta, -1e100), 1e100);
+        const double w = fma(zeta, zeta, 1.0);
+        const double sq = w * rsqrt_nr_t<2>(w);
+        const double t = copysign(rcp_nr_t<2>(fabs(zeta) + sq), zeta);
+        cc = rsqrt_nr_t<2>(fma(t, t, 1.0));
+        ss = t * cc;
+#pragma unroll
+        for (int u = 0; u < 2 * NUMAX; ++u) {
+            if (u < 2 * NU) {
+                const double x = ap[u], y = aq[u];
+                ap[u] = cc * x - ss * y;
+                aq[u] = ss * x + cc * y;
+            }
+        }
+    }
+}
+
+template <int NU_T>  // NU_T = 8: the n = 128 specialisation (no row guards); 0: ne / 16 at run time
+__global__ void __launch_bounds__(512) jacobi1s_kernel(const double* __restrict__ G, int n, int ne, double2* __restrict__ rotlog,
+                                                       int max_sweeps, double rel_tol, int* __restrict__ nsteps_out,
+                                                       double* __restrict__ Bout, unsigned short* __restrict__ pairtab) {
+    constexpr int NUMAX = 8;
+    extern __shared__ __align__(16) double Bm[];  // ne x ne, column-major
+    __shared__ int s_rot;
+    __shared__ double s_scale;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int wid = tid >> 5, ln = tid & 31, g = ln >> 3, r8 = ln & 7;
+    const int NU = NU_T ? NU_T : ne / 16, nblk = ne / 4;
+    const int slot = 4 * wid + g;
+
+    for (int e = tid; e < ne * ne; e += nt) {
+        const int j = e / ne, i = e - j * ne;
+        Bm[e] = (i < n && j < n) ? G[(size_t)j * n + i] : 0.0;  // G is symmetric: read it row-wise
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double gmax = 0.0;
+        for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(Bm[i * ne + i]));
+        s_scale = gmax;
+    }
+    __syncthreads();
+    const double floor_abs = 4.9303806576313238e-32 * s_scale * s_scale;  // (eps * max|diag|)^2
+    // the pair schedule of one sweep for the eigenvector replay: p | q << 8, 0xffff = idle slot
+    for (int e = tid; e < jacobi1s_steps_per_sweep(ne) * 64; e += nt) {
+        int p, q;
+        pairtab[e] = jacobi1s_pair(ne, e >> 6, e & 63, p, q) ? (unsigned short)(p | (q << 8)) : (unsigned short)0xffff;
+    }
+
+    auto load_col = [&](int col, double (&a)[2 * NUMAX]) {
+        const double* cp = Bm + col * ne + 2 * r8;
+#pragma unroll
+        for (int u = 0; u < NUMAX; ++u)
+            if (u < NU) {
+                const double2 x = *reinterpret_cast<const double2*>(cp + 16 * u);
+                a[2 * u] = x.x, a[2 * u + 1] = x.y;
+            }
+    };
+    auto store_col = [&](int col, const double (&a)[2 * NUMAX]) {
+        double* cp = Bm + col * ne + 2 * r8;
+#pragma unroll
+        for (int u = 0; u < NUMAX; ++u)
+            if (u < NU) *reinterpret_cast<double2*>(cp + 16 * u) = make_double2(a[2 * u], a[2 * u + 1]);
+    };
+
+    int step_base = 0;
+    const int sps = jacobi1s_steps_per_sweep(ne);
+    int rotated = 0;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep, step_base += sps) {
+        if (tid == 0) s_rot = 0;
+        rotated = 0;
+        // ---- the pairs inside the blocks
+#pragma unroll 1
+        for (int st = 0; st < 3; ++st) {
+            int p = 0, q = 0;
+            const bool active = jacobi1s_pair(ne, st, slot, p, q);
+            double ap[2 * NUMAX], aq[2 * NUMAX], cc, ss;
+            load_col(p, ap);
+            load_col(q, aq);
+            jacobi1s_rotate<NUMAX>(ap, aq, NU, active, floor_abs, rel_tol, cc, ss);
+            if (ss != 0.0) {
+                store_col(p, ap);
+                store_col(q, aq);
+                rotated = 1;
+            }
+            if (r8 == 0) rotlog[(size_t)(step_base + st) * 64 + slot] = make_double2(cc, ss);
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- block round-robin
+#pragma unroll 1
+        for (int sr = 0; sr < nblk - 1; ++sr) {
+            int p = 0, q = 0;
+            const bool active = jacobi1s_pair(ne, 3 + 4 * sr, slot, p, q);
+            const int qb = q - (g & 3);  // first column of block Y
+            double ap[2 * NUMAX], aq[2 * NUMAX], cc, ss;
+            load_col(p, ap);
+            bool xdirty = false;
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                const int qq = active ? qb + ((g + t) & 3) : 0;
+                load_col(qq, aq);
+                jacobi1s_rotate<NUMAX>(ap, aq, NU, active, floor_abs, rel_tol, cc, ss);
+                if (ss != 0.0) {
+                    store_col(qq, aq);
+                    xdirty = true;
+                }
+                if (r8 == 0) rotlog[(size_t)(step_base + 3 + 4 * sr + t) * 64 + slot] = make_double2(cc, ss);
+                __syncwarp();
+            }
+            if (xdirty) {
+                store_col(p, ap);
+                rotated = 1;
+            }
+            __syncthreads();
+        }
+        if (rotated) s_rot = 1;  // benign race: every writer stores the same value
+        __syncthreads();
+        const int nrot = s_rot;
+        __syncthreads();
+        if (nrot == 0) {
+            step_base += sps;
+            break;
+        }
+    }
+    if (tid == 0) *nsteps_out = step_base;
+    for (int e = tid; e < ne * ne; e += nt) Bout[e] = Bm[e];
+}
+
+// V = J_1 J_2 ... for the one-sided kernel's log: one WARP per row of V (the row lives in warp-private shared memory,
+// a step's ne / 2 rotations are disjoint: two slots per lane, one __syncwarp per step)
+__global__ void __launch_bounds__(128) jacobi1s_apply_kernel(const double2* __restrict__ rotlog, const int* __restrict__ nsteps,
+                                                            const unsigned short* __restrict__ pairtab, int n, int ne,
+                                                            double* __restrict__ V) {
+    __shared__ double rows[4][128];
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + wid;
+    if (b >= n) return;
+    double* row = rows[wid];
+    for (int j = ln; j < ne; j += 32) row[j] = (j == b) ? 1.0 : 0.0;
+    __syncwarp();
+    const int sps = jacobi1s_steps_per_sweep(ne);
+    const int S = *nsteps;
+    // the log lives in L2: fetch DEPTH steps at a time (rotations and pair schedule), then apply them, so that one L2
+    // round trip is paid per DEPTH steps
+    constexpr int DEPTH = 8;
+    int sst = 0;
+    for (int st0 = 0; st0 < S; st0 += DEPTH) {
+        double2 cs0[DEPTH], cs1[DEPTH];
+        unsigned pq0[DEPTH], pq1[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            cs0[d] = cs1[d] = make_double2(1.0, 0.0);
+            pq0[d] = pq1[d] = 0xffff;
+            if (st0 + d < S) {
+                int sd = sst + d;
+                sd = sd >= sps ? sd - sps : sd;
+                cs0[d] = rotlog[(size_t)(st0 + d) * 64 + ln];
+                cs1[d] = rotlog[(size_t)(st0 + d) * 64 + ln + 32];
+                pq0[d] = pairtab[sd * 64 + ln];
+                pq1[d] = pairtab[sd * 64 + ln + 32];
+            }
+        }
+        sst += DEPTH;
+        sst = sst >= sps ? sst - sps : sst;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            if (cs0[d].y != 0.0 && pq0[d] != 0xffff) {
+                const int p = pq0[d] & 255, q = pq0[d] >> 8;
+                const double vp = row[p], vq = row[q];
+                row[p] = cs0[d].x * vp - cs0[d].y * vq;
+                row[q] = cs0[d].y * vp + cs0[d].x * vq;
+            }
+            if (cs1[d].y != 0.0 && pq1[d] != 0xffff) {
+                const int p = pq1[d] & 255, q = pq1[d] >> 8;
+                const double vp = row[p], vq = row[q];
+                row[p] = cs1[d].x * vp - cs1[d].y * vq;
+                row[q] = cs1[d].y * vp + cs1[d].x * vq;
+            }
+            __syncwarp();
+        }
+    }
+    for (int j = ln; j < n; j += 32) V[(size_t)b * n + j] = row[j];
+}
+
+// lambda_i = v_i^T (G v_i) = v_i . b_i   (B = G V column-major with pitch ne; V row-major n x n, eigenvectors in columns)
+__global__ void __launch_bounds__(256) eig_rayleigh_kernel(const double* __restrict__ B, int ne, const double* __restrict__ V, int n,
+                                                           double* __restrict__ lambda) {
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + wid; i < n; i += gridDim.x * (blockDim.x >> 5)) {
+        double acc = 0.0;
+        for (int j = ln; j < n; j += 32) acc = fma(V[(size_t)j * n + i], B[(size_t)i * ne + j], acc);
+        acc = warp_sum(acc);
+        if (ln == 0) lambda[i] = acc;
+    }
+}
+
 // V = J_1 J_2 ... (rows of the identity transformed independently): CTA b owns row b of V.
 __global__ void __launch_bounds__(256) jacobi_apply_kernel(const double2* __restrict__ rotlog, const int* __restrict__ nrounds,
-                                                           int n, double* __restrict__ V) {
+                                                           int n, int ne, double* __restrict__ V) {
     extern __shared__ double row[];
-    const int ne = (n + 1) & ~1, half = ne / 2;
+    const int half = ne / 2;
     const int b = blockIdx.x;
     for (int j = threadIdx.x; j < ne; j += blockDim.x) row[j] = (j == b) ? 1.0 : 0.0;
     __syncthreads();
@@ -328,6 +589,8 @@ int eigh_configure(Ctx* c) {
     LQ_CUDA(c, cudaFuncGetAttributes(&fa, jacobi_kernel));
     LQ_CUDA(c, cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     c->max_smem - (int)fa.sharedSizeBytes));
+    LQ_CUDA(c, cudaFuncSetAttribute(jacobi1s_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
+    LQ_CUDA(c, cudaFuncSetAttribute(jacobi1s_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
     LQ_CUDA(c, cudaFuncGetAttributes(&fa, tsqr_leaf_kernel<16, 8>));
     LQ_CUDA(c, cudaFuncSetAttribute(tsqr_leaf_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     c->max_smem - (int)fa.sharedSizeBytes));
@@ -382,25 +645,48 @@ int gram(Ctx* c, const double* A, long long m, int n, double* G) {
 int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) {
     LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_UNSUPPORTED, "eigen-solver supports n <= 2048 (got %d)", n);
     LQ_TRY(eigh_configure(c));
-    const int ne = (n + 1) & ~1, ld = ne | 1, half = ne / 2;
     const int max_sweeps = 40;
-    const size_t need = ((size_t)ne * ld + 4) * sizeof(double) + (size_t)half * sizeof(double2) + 64;
-    const int use_global = need + 9216 > (size_t)c->max_smem;  // 9 KB of static shared memory in the kernel
-    DevBuf Aw, rot, nr, lam, Vraw;
-    LQ_TRY(Aw.alloc(c, use_global ? sizeof(double) * (size_t)ne * ld : 16));
-    LQ_TRY(rot.alloc(c, sizeof(double2) * (size_t)max_sweeps * (ne - 1 > 0 ? ne - 1 : 1) * (half > 0 ? half : 1)));
-    LQ_TRY(nr.alloc(c, 16));
-    LQ_TRY(lam.alloc(c, sizeof(double) * n));
-    LQ_TRY(Vraw.alloc(c, sizeof(double) * (size_t)n * n));
-    const size_t smem = use_global ? (size_t)half * sizeof(double2) + 64 : need;
     // a pair is rotated while |a_pq| > rel_tol * sqrt(a_pp a_qq); 4 eps stops the tail of sweeps that only chase
     // rounding noise (eigenvalues move by O(a_pq^2 / gap), the eigenvector basis stays a product of exact rotations)
     double rel_tol = 4.0 * 1.1102230246251565e-16;
     if (const char* env = getenv("LINALG_B200_JACOBI_TOL")) rel_tol = atof(env) * 1.1102230246251565e-16;
+    DevBuf Aw, rot, nr, lam, Vraw, ptab;
+    LQ_TRY(nr.alloc(c, 16));
+    LQ_TRY(lam.alloc(c, sizeof(double) * n));
+    LQ_TRY(Vraw.alloc(c, sizeof(double) * (size_t)n * n));
+    if (n <= 128 && getenv("LINALG_B200_JACOBI_TWO_SIDED") == nullptr) {
+        // one-sided kernel: columns in shared memory, padded to a multiple of 16
+        const int ne = (n + 15) / 16 * 16, half = ne / 2;
+        LQ_TRY(Aw.alloc(c, sizeof(double) * (size_t)ne * ne));
+        LQ_TRY(rot.alloc(c, sizeof(double2) * (size_t)(max_sweeps + 1) * jacobi1s_steps_per_sweep(ne) * 64));
+        LQ_TRY(ptab.alloc(c, sizeof(unsigned short) * (size_t)jacobi1s_steps_per_sweep(ne) * 64));
+        if (ne == 128)
+            jacobi1s_kernel<8><<<1, 512, sizeof(double) * (size_t)ne * ne, c->stream>>>(G, n, ne, rot.as<double2>(), max_sweeps, rel_tol,
+                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>());
+        else
+            jacobi1s_kernel<0><<<1, 512, sizeof(double) * (size_t)ne * ne, c->stream>>>(G, n, ne, rot.as<double2>(), max_sweeps, rel_tol,
+                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>());
+        LQ_CHECK_LAUNCH(c);
+        jacobi1s_apply_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(rot.as<double2>(), nr.as<int>(), ptab.as<unsigned short>(), n, ne,
+                                                                   Vraw.as<double>());
+        LQ_CHECK_LAUNCH(c);
+        eig_rayleigh_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(Aw.as<double>(), ne, Vraw.as<double>(), n, lam.as<double>());
+        LQ_CHECK_LAUNCH(c);
+        eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
+        LQ_CHECK_LAUNCH(c);
+        c->launches += 4;
+        return LQ_OK;
+    }
+    const int ne = (n + 1) & ~1, ld = ne | 1, half = ne / 2;
+    const size_t need = ((size_t)ne * ld + 4) * sizeof(double) + (size_t)half * sizeof(double2) + 64;
+    const int use_global = need + 9216 > (size_t)c->max_smem;  // 9 KB of static shared memory in the kernel
+    LQ_TRY(Aw.alloc(c, use_global ? sizeof(double) * (size_t)ne * ld : 16));
+    LQ_TRY(rot.alloc(c, sizeof(double2) * (size_t)max_sweeps * (ne - 1 > 0 ? ne - 1 : 1) * (half > 0 ? half : 1)));
+    const size_t smem = use_global ? (size_t)half * sizeof(double2) + 64 : need;
     jacobi_kernel<<<1, 1024, smem, c->stream>>>(G, n, Aw.as<double>(), use_global, rot.as<double2>(), max_sweeps, rel_tol,
                                                nr.as<int>(), lam.as<double>());
     LQ_CHECK_LAUNCH(c);
-    jacobi_apply_kernel<<<n, 128, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, Vraw.as<double>());
+    jacobi_apply_kernel<<<n, 128, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, ne, Vraw.as<double>());
     LQ_CHECK_LAUNCH(c);
     eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
     LQ_CHECK_LAUNCH(c);
