@@ -381,19 +381,20 @@ struct EventPool {
 int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
-    cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1];
+    cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1], s_merge = c->lane[2];
     const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
     DevBuf Tloc, G, W, W2, Ws, W2s;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
-    DevBuf Wearly;  // split-K partials of V^T C_next, produced on the aux stream while the Gram matrix is formed
-    const size_t wearly_bytes = sizeof(double) * NB_OUT * NB_OUT * 160;
+    DevBuf Wa, W2a;  // scratch of the aux stream (panel-wise application to the next outer block)
+    const bool pw_lookahead = getenv("LINALG_B200_NO_PANELWISE") == nullptr;
     if (lookahead) {
         LQ_TRY(Ws.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
         LQ_TRY(W2s.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
-        LQ_TRY(Wearly.alloc(c, wearly_bytes));
+        LQ_TRY(Wa.alloc(c, sizeof(double) * NB_IN * (size_t)NB_OUT));
+        LQ_TRY(W2a.alloc(c, sizeof(double) * NB_IN * (size_t)NB_OUT));
     }
     double* Tall;
     if (keep) {
@@ -425,6 +426,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         LQ_CUDA(c, cudaEventRecord(e0, s_main));
         LQ_CUDA(c, cudaStreamWaitEvent(s_side, e0, 0));
         LQ_CUDA(c, cudaStreamWaitEvent(s_aux, e0, 0));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_merge, e0, 0));
     }
     for (int blk = 0; blk < nblocks; ++blk) {
         const int k0 = blk * NB_OUT;
@@ -433,6 +435,16 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         double* Tblk = Tall + (size_t)blk * NB_OUT * NB_OUT;
         if (mk <= 0) continue;
         const int nin = kb / NB_IN;
+        const int ntr = npad - (k0 + kb);
+        const int nnext = std::min(NB_OUT, ntr);
+        const int nrest = ntr - nnext;
+        double* Ctr = A + (size_t)k0 * lda + k0 + kb;
+        // panel-wise look-ahead: every panel's own reflector (V_p, T_p) is applied to the columns of the NEXT outer
+        // block on the aux stream as soon as the panel exists, in the shadow of the following panels, so the chain
+        // never waits for the Gram matrix / T merge of the whole block (they move to the side stream, where only the
+        // big trailing update and the Q formation need the merged T)
+        const bool pw = lookahead && pw_lookahead && nnext > 0 && nin > 1;
+        cudaEvent_t ev_aux_done = nullptr;
         for (int ip = 0; ip < nin; ++ip) {
             const int c0 = k0 + ip * NB_IN;
             const int mp = m - c0;
@@ -442,6 +454,20 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             double* Tp = Tblk + (size_t)ip * NB_IN * NB_OUT + ip * NB_IN;  // diagonal block of the outer T
             const int ldtp = NB_OUT;
             LQ_TRY(panel_factor(c, Ap, lda, Vp, ldv, Tp, ldtp, mp, NB_IN));
+            if (pw) {
+                cudaEvent_t ev_p;
+                LQ_TRY(pool.make(c, &ev_p));
+                LQ_CUDA(c, cudaEventRecord(ev_p, s_main));
+                StreamScope aux(c, s_aux);
+                LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_p, 0));
+                if (ip == 0 && ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_rest_prev, 0));  // block b+1's columns were in rest(b-1)
+                LQ_TRY(apply_block_reflector(c, Vp, ldv, Tp, ldtp, true, mp, NB_IN, A + (size_t)c0 * lda + k0 + kb, lda, nnext,
+                                             Wa.as<double>(), W2a.as<double>()));
+                if (ip == nin - 1) {
+                    LQ_TRY(pool.make(c, &ev_aux_done));
+                    LQ_CUDA(c, cudaEventRecord(ev_aux_done, s_aux));
+                }
+            }
             const int nrem = k0 + kb - (c0 + NB_IN);
             if (nrem > 0)
                 LQ_TRY(apply_block_reflector(c, Vp, ldv, Tp, ldtp, true, mp, NB_IN, Ap + NB_IN, lda, nrem,
@@ -452,45 +478,18 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             LQ_CUDA(c, cudaEventRecord(btrace[blk].panels, s_main));
         }
         const double* Vb = V + (size_t)k0 * ldv + k0;
-        // the product V^T C_next does not need the merged T: start it on the aux stream now, next to the Gram matrix
-        int early_splits = 0;
-        long long early_stride = 0;
-        cudaEvent_t ev_early = nullptr;
-        {
-            const int ntr0 = npad - (k0 + kb);
-            const int nnext0 = std::min(NB_OUT, ntr0);
-            if (lookahead && nnext0 > 0 && nin > 1) {
-                cudaEvent_t ev_v;
-                LQ_TRY(pool.make(c, &ev_v));
-                LQ_CUDA(c, cudaEventRecord(ev_v, s_main));
-                StreamScope aux(c, s_aux);
-                LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_v, 0));
-                if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_aux, ev_rest_prev, 0));
-                const int rc = vtc_partials(c, kb, nnext0, mk, Vb, ldv, A + (size_t)k0 * lda + k0 + kb, lda, Wearly.as<double>(),
-                                            wearly_bytes, &early_splits, &early_stride);
-                if (rc == LQ_OK) {
-                    LQ_TRY(pool.make(c, &ev_early));
-                    LQ_CUDA(c, cudaEventRecord(ev_early, s_aux));
-                } else if (rc != LQ_ERR_UNSUPPORTED && rc != LQ_ERR_NOMEM) {
-                    return rc;
-                }
-            }
-        }
-        if (nin > 1) {
-            int grc = LQ_ERR_UNSUPPORTED;
-            if (kb == NB_OUT && getenv("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, kb, mk, Vb, ldv, Vb, ldv))
-                grc = vtc_cluster(c, 0, kb, kb, mk, Vb, ldv, Vb, ldv, nullptr, 0, G.as<double>());  // G = V^T V
-            if (grc == LQ_ERR_UNSUPPORTED)
-                grc = gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT);
-            LQ_TRY(grc);
+        // the T factor of the whole outer block: on the stream that needs it first
+        auto merge_block_t = [&]() -> int {
+            if (nin <= 1) return LQ_OK;
+            LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT));  // G = V^T V
             if (kb == 128) merge_t_kernel<128><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
             else merge_t_kernel<0><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
             LQ_CHECK_LAUNCH(c);
             LQ_COUNT_LAUNCH(c);
-        }
-        const int ntr = npad - (k0 + kb);
-        double* Ctr = A + (size_t)k0 * lda + k0 + kb;
+            return LQ_OK;
+        };
         if (!lookahead) {
+            LQ_TRY(merge_block_t());
             if (ntr > 0)
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, ntr, W.as<double>(),
                                              W2.as<double>()));
@@ -499,20 +498,17 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
                                              W.as<double>(), W2.as<double>()));
             continue;
         }
-        const int nnext = std::min(NB_OUT, ntr);
-        const int nrest = ntr - nnext;
         cudaEvent_t ev_panel;
         LQ_TRY(pool.make(c, &ev_panel));
         LQ_CUDA(c, cudaEventRecord(ev_panel, s_main));
         if (trace_blocks) btrace[blk].chain = ev_panel;
-        if (nnext > 0) {
-            if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
-            if (ev_early) {
-                LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_early, 0));
-                LQ_TRY(vtc_finish(c, Wearly.as<double>(), early_splits, early_stride, kb, nnext, Tblk, NB_OUT, true,
-                                  W2.as<double>()));
-                LQ_TRY(gemm(c, false, false, mk, nnext, kb, -1.0, Vb, ldv, W2.as<double>(), nnext, 1.0, Ctr, lda));
-            } else {
+        if (pw) {
+            // the next block's columns are complete once the aux stream has applied the last panel
+            LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_aux_done, 0));
+        } else {
+            LQ_TRY(merge_block_t());
+            if (nnext > 0) {
+                if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
                                              W2.as<double>()));
             }
@@ -521,9 +517,21 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             LQ_TRY(pool.make(c, &btrace[blk].next));
             LQ_CUDA(c, cudaEventRecord(btrace[blk].next, s_main));
         }
-        if (nrest > 0 || (B && nrhs_pad > 0)) {
+        {
+            // the merged T: on its own stream right after the panels (so that it is ready when the side stream's
+            // previous trailing update retires); then the side stream: trailing update beyond the next block, rhs
+            cudaEvent_t ev_after;
+            LQ_TRY(pool.make(c, &ev_after));
+            if (pw) {
+                StreamScope mg(c, s_merge);
+                LQ_CUDA(c, cudaStreamWaitEvent(s_merge, ev_panel, 0));
+                LQ_TRY(merge_block_t());
+                LQ_CUDA(c, cudaEventRecord(ev_after, s_merge));
+            } else {
+                LQ_CUDA(c, cudaEventRecord(ev_after, s_main));  // T merged on the main stream
+            }
             StreamScope side(c, s_side);
-            LQ_CUDA(c, cudaStreamWaitEvent(s_side, ev_panel, 0));
+            LQ_CUDA(c, cudaStreamWaitEvent(s_side, ev_after, 0));
             if (nrest > 0)
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr + nnext, lda, nrest,
                                              Ws.as<double>(), W2s.as<double>()));
