@@ -428,6 +428,80 @@ def test_pca_matches_numpy(ctx):
     assert np.abs(pcs.T @ pcs - np.eye(k)).max() <= 1e-10
 
 
+# ------------------------------------------------------------------ alternative kernels of the same rows
+@pytest.mark.parametrize("batch", [1, 2, 3, 1001, 4737])
+def test_batched32_pipelined_variant_is_bitwise_identical(ctx, batch):
+    """Variant 13 (R phase of pair n+1 interleaved with the Q phase of pair n, persistent warps) performs the same
+    operations in the same order as the default kernel: identical bits, ragged tails included."""
+    A = np.random.default_rng(500 + batch).standard_normal((batch, 32, 32))
+    if batch > 16:
+        A[3, :, 5] = 0.0           # skipped reflector (qr.py:79)
+        A[7, :, 9] = A[7, :, 2]    # dependent column
+    dA = ctx.upload(A)
+    out = {}
+    for v in (0, 13):
+        dQ, dR = ctx.upload(np.full_like(A, np.nan)), ctx.upload(np.full_like(A, np.nan))
+        ctx.call("lq_householder_qr_batched_dev", dA.ptr, batch, 32, 32, dQ.ptr, dR.ptr, v)
+        out[v] = (ctx.download(dQ, A.shape), ctx.download(dR, A.shape))
+    assert np.array_equal(out[0][0], out[13][0]) and np.array_equal(out[0][1], out[13][1])
+    Qo, Ro = orc.householder_qr_batched(A[: min(batch, 32)])
+    assert orc.rel_max_err(out[13][0][: len(Qo)], Qo) <= REL and orc.rel_max_err(out[13][1][: len(Ro)], Ro) <= REL
+
+
+@pytest.mark.parametrize("m", [33, 64, 300, 1000, 4096, 8192])
+def test_panel_kernels_agree(ctx, m):
+    """The three panel factorisations of the blocked path (barrier.cluster kernel, st.async kernels with 512 / 256
+    rows per CTA) produce the same R rows, unit-norm reflectors and compact-WY factor, and (I - V T V^T)^T A = [R; 0]."""
+    lda = 64
+    A = np.random.default_rng(m).standard_normal((m, 32))
+    if m == 300:
+        A[:, 7] = 0.0
+        A[:, 20] = A[:, 3]
+
+    def run(version):
+        buf = np.zeros((m, lda))
+        buf[:, :32] = A
+        dA, dV, dT = ctx.upload(buf), ctx.upload(np.zeros((m, lda))), ctx.upload(np.zeros((32, 128)))
+        ctx.call("lq_debug_panel", dA.ptr, lda, dV.ptr, lda, dT.ptr, 128, m, 32, version)
+        R = np.triu(ctx.download(dA, (m, lda))[:32, :32])
+        return R, ctx.download(dV, (m, lda))[:, :32].copy(), ctx.download(dT, (32, 128))[:, :32].copy()
+
+    ref = run(1)
+    scale = np.abs(A).max()
+    for version in (2, 3):
+        if m > 16 * (512 if version == 2 else 256):
+            continue
+        R, V, T = run(version)
+        assert orc.rel_max_err(R, ref[0]) <= 1e-13 and orc.rel_max_err(V, ref[1]) <= 1e-13 and orc.rel_max_err(T, ref[2]) <= 1e-12
+        QtA = A - V @ (T.T @ (V.T @ A))
+        assert np.abs(QtA[:32] - R).max() <= 1e-13 * scale * np.sqrt(m) and (m == 32 or np.abs(QtA[32:]).max() <= 1e-13 * scale * np.sqrt(m))
+
+
+def test_eigh_one_sided_matches_two_sided(ctx):
+    """n <= 128 runs the one-sided block round-robin Jacobi; LINALG_B200_JACOBI_TWO_SIDED selects the two-sided kernel."""
+    import os
+
+    for n, rows in ((128, 4096), (128, 100), (96, 500), (33, 40)):
+        M = np.random.default_rng(n + rows).standard_normal((rows, n))
+        G = M.T @ M
+        res = {}
+        for two in (False, True):
+            if two:
+                os.environ["LINALG_B200_JACOBI_TWO_SIDED"] = "1"
+            try:
+                dG, dl, dV = ctx.upload(G), ctx.alloc(8 * n), ctx.alloc(8 * n * n)
+                ctx.call("lq_eigh_dev", dG.ptr, n, dl.ptr, dV.ptr)
+                res[two] = (ctx.download(dl, (n,)), ctx.download(dV, (n, n)))
+            finally:
+                os.environ.pop("LINALG_B200_JACOBI_TWO_SIDED", None)
+        ref = np.linalg.eigvalsh(G)[::-1]
+        for lam, V in res.values():
+            assert np.max(np.abs(lam - ref)) <= 1e-12 * ref[0]
+            assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-12
+            assert np.abs(G @ V - V * lam).max() <= 1e-11 * ref[0]
+        assert np.max(np.abs(res[False][0] - res[True][0])) <= 1e-12 * ref[0]
+
+
 def test_no_cpu_fallback_loaded(ctx):
     """The numbers above came from the in-tree CUDA library: it is the loaded object and it counted launches."""
     from linalg_b200 import _native
