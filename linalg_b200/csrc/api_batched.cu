@@ -67,7 +67,8 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
     if (m == 32 && n == 32 && variant >= 0) {
         switch (variant) {
             case 0:
-            case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // default: 2 Newton steps
+            case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // default: reciprocal seeded from the raw rsqrt
+            case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
             case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
             case 2: return launch_hh32<1, 2, 4, false, 2>(c, st, A, batch, Q, R);

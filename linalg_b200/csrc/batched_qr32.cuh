@@ -137,11 +137,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const double ssc = fmax(ss, 1e-300);
         // ||x|| = ss * rsqrt(ss): the Newton-refined rsqrt is good to 2.7e-16 (lq_probe 13), so the extra
         // correction step of sqrt_nr_t would only polish the last bit of R[j][j] while sitting on the serial chain
-        const double nrm = ssc * rsqrt_nr_t<NR>(ssc);
+        double nrm, beta;
+        if (NR >= 0) {
+            nrm = ssc * rsqrt_nr_t<(NR >= 0 ? NR : 2)>(ssc);
+        } else {
+            // NR < 0: y = 1/||x||, beta = 2 / v^T v = y^2 / (1 + |x0| y); the reciprocal is seeded from the UNREFINED y,
+            // so its MUFU runs beside the Newton steps of y instead of behind them (shorter serial chain)
+            const double ax0 = fabs(x0);
+            double y = rsqrt_seed(ssc);
+            double u = rcp_seed(fma(ax0, y, 1.0));
+            const double hx = 0.5 * ssc;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const double e = fma(-hx * y, y, 0.5);
+                y = fma(y, e, y);
+            }
+            nrm = ssc * y;
+            const double D = fma(ax0, y, 1.0);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const double e = fma(-D, u, 1.0);
+                u = fma(u, e, u);
+            }
+            beta = (y * y) * u;
+        }
         const bool skip = nrm < kEps;  // qr.py:79-80
         const double alpha = copysign(nrm, x0);
         const double v0 = x0 + alpha;
-        const double beta = skip ? 0.0 : rcp_nr_t<NR>(nrm * fabs(v0));  // 2 / v^T v
+        if (NR >= 0) beta = rcp_nr_t<(NR >= 0 ? NR : 2)>(nrm * fabs(v0));  // 2 / v^T v
+        beta = skip ? 0.0 : beta;
         if (lm == 0) {
             betas[j] = beta;
             v0s[j] = v0;

@@ -811,6 +811,168 @@ int gemm_rank(Ctx* c, long long M, int N, int K, double alpha, const double* A, 
     return LQ_OK;
 }
 
+
+// ------------------------------------------------------------------ rank-K update  C += alpha * A * B   (NN, small K)
+// The block-reflector applications of the blocked QR end in C -= V W with K = 128: a 128 x 128 tile spends as long in
+// its prologue (first TMA round trip) and epilogue as in 3 of its 8 k-tiles, and one CTA per SM cannot hide either
+// (DMMA pipe 70 %).  This kernel halves the tile (128 x 64: 64 accumulator registers, a 100 KB operand ring), so TWO
+// CTAs share an SM and one CTA's prologue / epilogue runs under the other's main loop.  Same ingredients as
+// gemm_dmma_kernel: K-major A tiles as one swizzled 2-D TMA box per stage, B rows as bulk copies, mma.sync m16n8k8.f64,
+// the result leaves through the TMA engine as one bulk reduce-add per row (no read-back of C, one writer per element).
+constexpr int UBN = 64;
+constexpr int UPB = UBN + 4;                 // pitch of a [k][n] B tile
+constexpr int U_STAGES = 4;
+constexpr int U_STAGE_BYTES = 25600;         // 16 KiB A box + 16 x 68 doubles of B, rounded to 1 KiB (swizzle alignment)
+constexpr int U_EPI_PITCH = UBN + 8;         // staged C row (a quarter-warp's 16-byte stores hit distinct banks)
+constexpr size_t UPD_SMEM = (size_t)U_STAGES * U_STAGE_BYTES + 2 * U_STAGES * sizeof(uint64_t) + 1024;
+static_assert(BM * BK * 8 + BK * UPB * 8 <= U_STAGE_BYTES, "stage holds an A box and a B tile");
+static_assert((size_t)BM * U_EPI_PITCH * 8 <= (size_t)U_STAGES * U_STAGE_BYTES, "the staged C tile reuses the operand ring");
+
+struct UpdArgs {
+    const double* B;
+    double* C;
+    long long M;
+    int N, K;
+    int ldb, ldc;
+    double alpha;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_upd_kernel(const UpdArgs g, const __grid_constant__ CUtensorMap mapA) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)U_STAGES * U_STAGE_BYTES);
+    uint64_t* empty = full + U_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * UBN;
+    const int mvalid = (int)min((long long)BM, g.M - m0);
+    const int nvalid = min(UBN, g.N - n0);
+    const int nkt = g.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < U_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        // ===================== producer =====================
+        const uint32_t bytes = (uint32_t)(BM * BK * 8) + (uint32_t)(BK * nvalid * 8);
+        for (int it = 0; it < nkt; ++it) {
+            const int s = it % U_STAGES;
+            const uint32_t ph = (it / U_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            double* sA = reinterpret_cast<double*>(smem_raw + (size_t)s * U_STAGE_BYTES);
+            double* sB = sA + BM * BK;
+            const int k0 = it * BK;
+            if (lane == 0) mbar_expect_tx(&full[s], bytes);
+            __syncwarp();
+            if (lane == 0) tma_load_2d(sA, &mapA, k0, (int)m0, &full[s]);
+            if (lane >= 16) {
+                const int kk = lane - 16;
+                bulk_g2s(sB + kk * UPB, g.B + (long long)(k0 + kk) * g.ldb + n0, nvalid * 8, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: 4 (m) x 2 (n) warps, 32 x 32 each =====================
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gq = lane >> 2, tq = lane & 3;
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+
+    for (int it = 0; it < nkt; ++it) {
+        const int s = it % U_STAGES;
+        const uint32_t ph = (it / U_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const double* sA = reinterpret_cast<const double*>(smem_raw + (size_t)s * U_STAGE_BYTES);
+        const double* sB = sA + BM * BK;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            const int kA = ks * 8 + tq;
+            double bf[4][2];
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+                const int c = wn * 32 + jn * 8 + gq;
+                bf[jn][0] = sB[kA * UPB + c];
+                bf[jn][1] = sB[(kA + 4) * UPB + c];
+            }
+#pragma unroll
+            for (int im = 0; im < 2; ++im) {
+                double af[4];
+                const int r = wm * 32 + im * 16 + gq;
+                af[0] = sA[sw_idx(r, gq, kA)];
+                af[1] = sA[sw_idx(r + 8, gq, kA)];
+                af[2] = sA[sw_idx(r, gq, kA + 4)];
+                af[3] = sA[sw_idx(r + 8, gq, kA + 4)];
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af, bf[jn]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ===================== epilogue: stage the tile, one bulk reduce-add per row =====================
+    consumer_bar_sync();  // every consumer warp is done reading the operand stages
+    double* stg = reinterpret_cast<double*>(smem_raw);
+#pragma unroll
+    for (int im = 0; im < 2; ++im)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = wm * 32 + im * 16 + gq + half * 8;
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+                const int c = wn * 32 + jn * 8 + 2 * tq;
+                *reinterpret_cast<double2*>(stg + r * U_EPI_PITCH + c) =
+                    make_double2(g.alpha * acc[im][jn][half * 2 + 0], g.alpha * acc[im][jn][half * 2 + 1]);
+            }
+        }
+    fence_proxy_async();
+    consumer_bar_sync();
+    if (lane < 16) {
+        const int r = warp * 16 + lane;
+        if (r < mvalid) bulk_red_add_f64(g.C + (m0 + r) * (long long)g.ldc + n0, stg + r * U_EPI_PITCH, (uint32_t)nvalid * 8u);
+    }
+    bulk_commit();
+    bulk_wait_read<0>();
+}
+
+// C += alpha * A * B for row-major A (M x K, lda), B (K x N, ldb), K a small multiple of 16; LQ_ERR_UNSUPPORTED otherwise
+int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
+                int ldc) {
+    if (getenv("LINALG_B200_NO_UPD_GEMM")) return LQ_ERR_UNSUPPORTED;
+    if (K % BK != 0 || K < BK || K > 512 || (N % 2) != 0 || (ldc % 2) != 0 || !aligned16(C) || M < BM || N < UBN)
+        return LQ_ERR_UNSUPPORTED;
+    const long long tm = (M + BM - 1) / BM;
+    const int tn = (N + UBN - 1) / UBN;
+    if (tm * tn < 2LL * c->sm_count) return LQ_ERR_UNSUPPORTED;  // small outputs: the split-K / one-tile paths
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(gemm_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+        configured[c->device] = true;
+    }
+    CUtensorMap mapA;
+    LQ_TRY(make_kmajor_map(c, &mapA, A, M, K, lda));
+    UpdArgs g;
+    g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha;
+    dim3 grid((unsigned)tn, (unsigned)tm);
+    gemm_upd_kernel<<<grid, GEMM_THREADS, UPD_SMEM, c->stream>>>(g, mapA);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
 int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, const double* A, int lda, const double* B,
          int ldb, double beta, double* C, int ldc) {
     if (M <= 0 || N <= 0) return LQ_OK;
@@ -835,6 +997,10 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
     if (!ta && !tb && Kmain == K) {
         rc = gemm_rank(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
         if (rc != LQ_ERR_UNSUPPORTED) return rc;
+        if (beta == 1.0) {
+            rc = gemm_update(c, M, N, K, alpha, A, lda, B, ldb, C, ldc);
+            if (rc != LQ_ERR_UNSUPPORTED) return rc;
+        }
     }
     if (ta && tb) rc = launch_fast<true, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (ta) rc = launch_fast<true, false>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
