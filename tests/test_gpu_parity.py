@@ -432,18 +432,19 @@ def test_pca_matches_numpy(ctx):
 @pytest.mark.parametrize("batch", [1, 2, 3, 1001, 4737])
 def test_batched32_pipelined_variant_is_bitwise_identical(ctx, batch):
     """Variant 13 (R phase of pair n+1 interleaved with the Q phase of pair n, persistent warps) performs the same
-    operations in the same order as the default kernel: identical bits, ragged tails included."""
+    operations in the same order as the one-shot kernel with the same scalar chain (variant 6): identical bits, ragged
+    tails included."""
     A = np.random.default_rng(500 + batch).standard_normal((batch, 32, 32))
     if batch > 16:
         A[3, :, 5] = 0.0           # skipped reflector (qr.py:79)
         A[7, :, 9] = A[7, :, 2]    # dependent column
     dA = ctx.upload(A)
     out = {}
-    for v in (0, 13):
+    for v in (6, 13):
         dQ, dR = ctx.upload(np.full_like(A, np.nan)), ctx.upload(np.full_like(A, np.nan))
         ctx.call("lq_householder_qr_batched_dev", dA.ptr, batch, 32, 32, dQ.ptr, dR.ptr, v)
         out[v] = (ctx.download(dQ, A.shape), ctx.download(dR, A.shape))
-    assert np.array_equal(out[0][0], out[13][0]) and np.array_equal(out[0][1], out[13][1])
+    assert np.array_equal(out[6][0], out[13][0]) and np.array_equal(out[6][1], out[13][1])
     Qo, Ro = orc.householder_qr_batched(A[: min(batch, 32)])
     assert orc.rel_max_err(out[13][0][: len(Qo)], Qo) <= REL and orc.rel_max_err(out[13][1][: len(Ro)], Ro) <= REL
 
