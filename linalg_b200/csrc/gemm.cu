@@ -835,6 +835,7 @@ struct UpdArgs {
     int N, K;
     int ldb, ldc;
     double alpha;
+    int overwrite;  // 0: C += alpha A B (bulk reduce-add), 1: C = alpha A B (bulk store)
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_upd_kernel(const UpdArgs g, const __grid_constant__ CUtensorMap mapA) {
@@ -942,15 +943,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_upd_kernel(const UpdArgs
     consumer_bar_sync();
     if (lane < 16) {
         const int r = warp * 16 + lane;
-        if (r < mvalid) bulk_red_add_f64(g.C + (m0 + r) * (long long)g.ldc + n0, stg + r * U_EPI_PITCH, (uint32_t)nvalid * 8u);
+        if (r < mvalid) {
+            double* dst = g.C + (m0 + r) * (long long)g.ldc + n0;
+            if (g.overwrite) bulk_s2g(dst, stg + r * U_EPI_PITCH, (uint32_t)nvalid * 8u);
+            else bulk_red_add_f64(dst, stg + r * U_EPI_PITCH, (uint32_t)nvalid * 8u);
+        }
     }
     bulk_commit();
     bulk_wait_read<0>();
 }
 
-// C += alpha * A * B for row-major A (M x K, lda), B (K x N, ldb), K a small multiple of 16; LQ_ERR_UNSUPPORTED otherwise
+// C (+)= alpha * A * B for row-major A (M x K, lda), B (K x N, ldb), K a small multiple of 16; LQ_ERR_UNSUPPORTED otherwise
 int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
-                int ldc) {
+                int ldc, bool overwrite) {
     if (getenv("LINALG_B200_NO_UPD_GEMM")) return LQ_ERR_UNSUPPORTED;
     if (K % BK != 0 || K < BK || K > 512 || (N % 2) != 0 || (ldc % 2) != 0 || !aligned16(C) || M < BM || N < UBN)
         return LQ_ERR_UNSUPPORTED;
@@ -965,7 +970,7 @@ int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A
     CUtensorMap mapA;
     LQ_TRY(make_kmajor_map(c, &mapA, A, M, K, lda));
     UpdArgs g;
-    g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha;
+    g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.ldb = ldb; g.ldc = ldc; g.alpha = alpha; g.overwrite = overwrite ? 1 : 0;
     dim3 grid((unsigned)tn, (unsigned)tm);
     gemm_upd_kernel<<<grid, GEMM_THREADS, UPD_SMEM, c->stream>>>(g, mapA);
     LQ_CHECK_LAUNCH(c);
@@ -995,12 +1000,13 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
     }
     int rc;
     if (!ta && !tb && Kmain == K) {
-        rc = gemm_rank(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-        if (rc != LQ_ERR_UNSUPPORTED) return rc;
-        if (beta == 1.0) {
-            rc = gemm_update(c, M, N, K, alpha, A, lda, B, ldb, C, ldc);
+        // small K: the two-CTAs-per-SM kernel (in-place accumulation or plain product), then the B-stationary walk
+        if (beta == 1.0 || beta == 0.0) {
+            rc = gemm_update(c, M, N, K, alpha, A, lda, B, ldb, C, ldc, beta == 0.0);
             if (rc != LQ_ERR_UNSUPPORTED) return rc;
         }
+        rc = gemm_rank(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        if (rc != LQ_ERR_UNSUPPORTED) return rc;
     }
     if (ta && tb) rc = launch_fast<true, true>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);
     else if (ta) rc = launch_fast<true, false>(c, M, N, Kmain, alpha, A, lda, B, ldb, beta, C, ldc);

@@ -574,6 +574,157 @@ __global__ void __launch_bounds__(1024) chol_upper_kernel(const double* __restri
 
 constexpr size_t CHOL_SMEM = 128 * 129 * sizeof(double);
 
+// ---- register-resident versions for n <= 128 (the CholeskyQR2 path of TSQR runs two of each per call; the generic
+// kernels above cost 0.20 + 0.36 ms, a fifth of the whole 2^20 x 128 TSQR)
+//
+// Inverse of an upper-triangular R: warp w solves the columns w, w + 32, w + 64, w + 96 of R X = I together (four
+// independent recurrences interleaved); lane l holds rows l + 32 u of each right-hand side in registers, R sits in
+// shared memory (odd pitch: a column walk is conflict free), 1 / R_kk is formed once.  Column-oriented back
+// substitution: x_k is broadcast from its owner lane, every lane updates its rows above k.
+__global__ void __launch_bounds__(1024) triu_inverse128_kernel(const double* __restrict__ R, int n, double* __restrict__ Rinv) {
+    extern __shared__ double ti_sm[];
+    double (*S)[129] = reinterpret_cast<double (*)[129]>(ti_sm);
+    __shared__ double dinv[128];
+    const int tid = threadIdx.x, w = tid >> 5, ln = tid & 31;
+    for (int e = tid; e < 128 * 128; e += 1024) {
+        const int i = e >> 7, k = e & 127;
+        S[i][k] = (i < n && k < n) ? R[(size_t)i * n + k] : ((i == k) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (tid < 128) dinv[tid] = 1.0 / S[tid][tid];
+    __syncthreads();
+    double x[4][4];  // [column c = w + 32 cc][row block u]: row ln + 32 u
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[cc][u] = (ln + 32 * u == w + 32 * cc) ? 1.0 : 0.0;
+#pragma unroll
+    for (int ub = 3; ub >= 0; --ub) {
+        for (int kk = 31; kk >= 0; --kk) {
+            const int k = 32 * ub + kk;
+            const double dk = dinv[k];
+            double rk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rk[u] = (u <= ub) ? S[ln + 32 * u][k] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                if (cc < ub) continue;  // column w + 32 cc < 32 (cc + 1) <= k: x_k = 0 (compile-time skip of whole blocks)
+                const double xk = __shfl_sync(0xffffffffu, x[cc][ub], kk) * dk;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (u < ub) x[cc][u] = fma(-rk[u], xk, x[cc][u]);
+                    else if (u == ub) x[cc][u] = (ln == kk) ? xk : ((ln < kk) ? fma(-rk[u], xk, x[cc][u]) : x[cc][u]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int col = w + 32 * cc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = ln + 32 * u;
+            if (i < n && col < n) Rinv[(size_t)i * n + col] = (i <= col) ? x[cc][u] : 0.0;
+        }
+    }
+}
+
+// Upper Cholesky factor for n <= 128 with the matrix in registers: thread (ty, tx) of a 32 x 32 block owns the
+// elements (ty + 32 a, tx + 32 b).  Per column: the diagonal owner publishes the pivot, the owners of row j publish
+// the scaled row, everybody updates its 16 elements (8 shared loads, 16 FMAs, no index arithmetic).  Same outputs
+// as chol_upper_kernel.
+__global__ void __launch_bounds__(1024) chol_upper128_kernel(const double* __restrict__ G, int n, double* __restrict__ R,
+                                                             double* __restrict__ stat) {
+    __shared__ double rowbuf[2][128];
+    __shared__ double s_piv[2];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double a[4][4];
+#pragma unroll
+    for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) {
+            const int i = ty + 32 * ia, k = tx + 32 * ib;
+            a[ia][ib] = (i < n && k < n) ? G[(size_t)i * n + k] : ((i == k) ? 1.0 : 0.0);
+        }
+    double dmax = 0.0, pmin = 1e300;
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < n; ++j) dmax = fmax(dmax, G[(size_t)j * n + j]);
+    }
+    int bad = 0;
+#pragma unroll
+    for (int ja = 0; ja < 4; ++ja) {
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = 32 * ja + jj, par = j & 1;
+            if (ty == jj && tx == jj) s_piv[par] = a[ja][ja];
+            __syncthreads();
+            const double piv = s_piv[par];
+            if (!(piv > 0.0)) {  // also catches NaN; uniform
+                bad = 1;
+                break;
+            }
+            if (j < n) pmin = fmin(pmin, piv);  // (rows >= n are identity padding)
+            const double rd = rsqrt_nr_t<2>(piv);
+            if (ty == jj) {
+                // my elements of row j, scaled; columns left of the diagonal are not part of R
+#pragma unroll
+                for (int ib = 0; ib < 4; ++ib) {
+                    const int k = tx + 32 * ib;
+                    double v = a[ja][ib] * rd;
+                    if (k == j) v = piv * rd;
+                    if (k < j) v = 0.0;
+                    a[ja][ib] = v;
+                    rowbuf[par][k] = v;
+                }
+            }
+            __syncthreads();
+            double ri[4], rk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ri[q] = rowbuf[par][ty + 32 * q];
+                rk[q] = rowbuf[par][tx + 32 * q];
+            }
+#pragma unroll
+            for (int ia = 0; ia < 4; ++ia) {
+                if (ia < ja) continue;
+                const int i = ty + 32 * ia;
+#pragma unroll
+                for (int ib = 0; ib < 4; ++ib) {
+                    if (ib < ja) continue;
+                    if (i > j) a[ia][ib] = fma(-ri[ia], rk[ib], a[ia][ib]);  // rows below j (columns left of j see rk = 0)
+                }
+            }
+        }
+        if (bad) break;
+    }
+#pragma unroll
+    for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) {
+            const int i = ty + 32 * ia, k = tx + 32 * ib;
+            if (i < n && k < n) R[(size_t)i * n + k] = (k >= i) ? a[ia][ib] : 0.0;
+        }
+    if (threadIdx.x == 0) {
+        stat[0] = bad ? 1.0 : 0.0;
+        stat[1] = bad ? 1e300 : dmax / pmin;
+    }
+}
+
+int launch_triu_inverse(Ctx* c, const double* R, int n, double* Rinv) {
+    if (n <= 128) {
+        static bool configured[64] = {};
+        if (!configured[c->device]) {
+            LQ_CUDA(c, cudaFuncSetAttribute(triu_inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
+            configured[c->device] = true;
+        }
+        triu_inverse128_kernel<<<1, 1024, 128 * 129 * 8, c->stream>>>(R, n, Rinv);
+    } else {
+        triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R, n, Rinv);
+    }
+    LQ_CHECK_LAUNCH(c);
+    return LQ_OK;
+}
+
+
 __global__ void __launch_bounds__(256) scale_cols_tall_kernel(double* __restrict__ M, long long rows, int n,
                                                               const double* __restrict__ sgn) {
     const long long total = rows * n;
@@ -743,7 +894,7 @@ static int tsqr_householder(Ctx* c, const double* A, long long m, int n, double*
     };
     // pass 1
     LQ_TRY(reduce_R(A, R1.as<double>()));
-    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R1.as<double>(), n, Rinv.as<double>());
+    LQ_TRY(launch_triu_inverse(c, R1.as<double>(), n, Rinv.as<double>()));
     LQ_CHECK_LAUNCH(c);
     LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, Rinv.as<double>(), n, 0.0, Q1.as<double>(), n));
     // pass 2 (refinement)
@@ -754,7 +905,7 @@ static int tsqr_householder(Ctx* c, const double* A, long long m, int n, double*
     //   sign_fix made diag(R2) > 0; R1's diagonal sign decides the final flip.
     LQ_TRY(gemm(c, false, false, n, n, n, 1.0, R2.as<double>(), n, R1.as<double>(), n, 0.0, R, n));
     // Q = Q1 (S R2)^{-1} ... then flip so that diag(R) > 0
-    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R2.as<double>(), n, Rinv.as<double>());
+    LQ_TRY(launch_triu_inverse(c, R2.as<double>(), n, Rinv.as<double>()));
     LQ_CHECK_LAUNCH(c);
     sign_fix_R_kernel<<<1, 256, 0, c->stream>>>(R, n, sgn.as<double>());                  // R <- S2 R
     scale_cols_kernel<<<grid_for(c, (long long)n * n), 256, 0, c->stream>>>(Rinv.as<double>(), n, sgn.as<double>());  // Rinv <- Rinv S2
@@ -785,22 +936,24 @@ static int tsqr_cholqr2(Ctx* c, const double* A, long long m, int n, double* Q, 
     // pass 1
     LQ_TRY(gram(c, A, m, n, G.as<double>()));
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
-    chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
+    if (n <= 128 && !getenv("LINALG_B200_OLD_CHOL")) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
+    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
     LQ_CUDA(c, cudaMemcpyAsync(hstat, stat.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LQ_CUDA(c, cudaStreamSynchronize(c->stream));
     if (hstat[0] != 0.0 || !(hstat[1] < 1e10)) return LQ_OK;  // ill-conditioned: caller falls back (same on every rank)
     LQ_TRY(Q1.alloc(c, sizeof(double) * (size_t)m * n));
-    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R1.as<double>(), n, Rinv.as<double>());
+    LQ_TRY(launch_triu_inverse(c, R1.as<double>(), n, Rinv.as<double>()));
     LQ_CHECK_LAUNCH(c);
     LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, Rinv.as<double>(), n, 0.0, Q1.as<double>(), n));
     // pass 2
     LQ_TRY(gram(c, Q1.as<double>(), m, n, G.as<double>()));
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
-    chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
+    if (n <= 128 && !getenv("LINALG_B200_OLD_CHOL")) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
+    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
     LQ_CHECK_LAUNCH(c);
-    triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R2.as<double>(), n, Rinv.as<double>());
+    LQ_TRY(launch_triu_inverse(c, R2.as<double>(), n, Rinv.as<double>()));
     LQ_CHECK_LAUNCH(c);
     c->launches += 3;
     LQ_TRY(gemm(c, false, false, n, n, n, 1.0, R2.as<double>(), n, R1.as<double>(), n, 0.0, R, n));
