@@ -95,7 +95,7 @@ struct GemmArgs {
 // BT: B is stored N x K (op(B) = B^T)  -> shared tile [n][k]   ("K-major")
 // 9 warps: registers are granted per 4-warp group, so a 288-thread block is capped at 168 registers/thread; the
 // main loop therefore keeps only ONE A fragment live at a time (128 accumulator + 8 + 16 fragment registers).
-template <bool AT, bool BT>
+template <bool AT, bool BT, bool SK = false>  // SK: skinny outputs, bands without valid rows / columns issue no DMMA
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_dmma_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ unsigned char smem_dyn[];
@@ -185,6 +185,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
     }
 
+    // SK instantiation (the V^T C products of the panel chain have 32 valid rows): 16-row / 8-column bands without a
+    // valid element issue no DMMA (warp-uniform tests), so a 32 x 96 product costs a fraction of a full tile's pipe time;
+    // kept out of the general instantiations, where the predicates cost 9 % on 4096^3
+    const int im_lim = min(4, max(0, (mvalid - wm * 64 + 15) >> 4));
+    const int jn_lim = min(4, max(0, (nvalid - wn * 32 + 7) >> 3));
     for (int it = 0; it < nkt; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
 #pragma unroll
             for (int im = 0; im < 4; ++im) {
+                if (SK && im >= im_lim) continue;
                 double af[4];
                 const int r = wm * 64 + im * 16 + gq;
                 if (AT) {
@@ -222,7 +228,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     af[3] = sA[sw_idx(r + 8, gq, kA + 4)];
                 }
 #pragma unroll
-                for (int jn = 0; jn < 4; ++jn) dmma_16x8x8(acc[im][jn], af, bf[jn]);
+                for (int jn = 0; jn < 4; ++jn)
+                    if (!SK || jn < jn_lim) dmma_16x8x8(acc[im][jn], af, bf[jn]);
             }
         }
         __syncwarp();
@@ -412,10 +419,12 @@ struct Partials {
 template <bool AT, bool BT>
 int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const double* A, int lda, const double* B, int ldb,
                 double beta, double* C, int ldc, Partials* parts = nullptr) {
-    auto kern = gemm_dmma_kernel<AT, BT>;
+    const bool skinny = AT && !BT && (M <= 64 || N <= 96);
+    auto kern = skinny ? gemm_dmma_kernel<AT, BT, AT && !BT> : gemm_dmma_kernel<AT, BT, false>;
     static bool configured[64] = {};
     if (!configured[c->device]) {
-        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        LQ_CUDA(c, cudaFuncSetAttribute(gemm_dmma_kernel<AT, BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        LQ_CUDA(c, cudaFuncSetAttribute(gemm_dmma_kernel<AT, BT, AT && !BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         configured[c->device] = true;
     }
     const long long tm = (M + BM - 1) / BM;
