@@ -290,7 +290,8 @@ int launch_cluster(Ctx* c, Kern kern, int cs, int threads, Args... args) {
 }
 
 // version: 0 = default choice, 1 = barrier.cluster kernel (panel.cuh), 2 = st.async kernel (panel2.cuh), 16 rows per lane,
-// 3 = st.async kernel with 8 rows per lane (256 rows per CTA)
+// 3 = st.async kernel with 8 rows per lane (256 rows per CTA), 4 = st.async kernels for every height (256 rows per CTA up to
+// 4096 rows, 512 above)
 int panel_factor_v(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb, int version) {
     using Cfg = PanelCfg<4, 16>;
     const int maxcs = detect_max_cluster(c);
@@ -313,7 +314,7 @@ int panel_factor_v(Ctx* c, double* A, int lda, double* V, int ldv, double* T, in
             while (cs * Panel2Cfg<8>::ROWS_PER_CTA < mp) cs *= 2;
             return launch_cluster(c, panel2_cluster_kernel<8, false>, cs, P2_THREADS, A, lda, V, ldv, T, ldt, mp, (long long*)nullptr);
         }
-        if (version == 2 && mp <= maxcs * Panel2Cfg<16>::ROWS_PER_CTA) {
+        if ((version == 2 || version == 4) && mp <= maxcs * Panel2Cfg<16>::ROWS_PER_CTA) {
             int cs = 1;
             while (cs * Panel2Cfg<16>::ROWS_PER_CTA < mp) cs *= 2;
             return launch_cluster(c, panel2_cluster_kernel<16, false>, cs, P2_THREADS, A, lda, V, ldv, T, ldt, mp, (long long*)nullptr);
