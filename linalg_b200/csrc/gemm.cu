@@ -1077,25 +1077,6 @@ int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int
     return LQ_OK;
 }
 
-// first half only: the split-K partial sums of V^T C into the caller's workspace (on the CURRENT stream of the
-// context); vtc_finish() later reduces them and applies op(T).  Returns LQ_ERR_UNSUPPORTED when the shape needs the
-// generic path (the caller then uses gemm_vtc_apply_t).
-int vtc_partials(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, double* ws,
-                 size_t ws_bytes, int* splits, long long* stride) {
-    const int Kmain = mk - mk % BK;
-    const bool fast = kb <= 128 && Kmain >= BK && Kmain == mk && aligned16(V) && aligned16(Cm) && (ldv % 2 == 0) &&
-                      (ldc % 2 == 0) && (kb % 4 == 0) && (nc % 2 == 0) && !getenv("LINALG_B200_NO_FAST_GEMM");
-    if (!fast) return LQ_ERR_UNSUPPORTED;
-    Partials parts;
-    parts.ext = ws;
-    parts.ext_bytes = ws_bytes;
-    LQ_TRY((launch_fast<true, false>(c, kb, nc, Kmain, 1.0, V, ldv, Cm, ldc, 0.0, nullptr, nc, &parts)));
-    if (parts.ptr != ws) return LQ_ERR_NOMEM;  // workspace too small: must not happen with the sizes used by the caller
-    *splits = parts.splits;
-    *stride = parts.stride;
-    return LQ_OK;
-}
-
 }  // namespace lq
 
 using namespace lq;

@@ -15,9 +15,7 @@ int gemm(Ctx* c, bool transa, bool transb, long long m, int n, int k, double alp
 int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
                      int ldt, bool trans_t, double* W2);
 
-// the same in two phases (partials on one stream, reduction + op(T) on another once T exists)
-int vtc_partials(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, double* ws,
-                 size_t ws_bytes, int* splits, long long* stride);
+// second phase of the above (reduction of the split-K partial sums + op(T)), used by gemm_vtc_apply_t
 int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int kb, int nc, const double* T, int ldt,
                bool trans_t, double* W2);
 
