@@ -1,7 +1,8 @@
 // Modified Gram-Schmidt (linalg/qr.py:14-49) for a single matrix that does not fit one CTA's
 // shared memory.  Right-looking order (identical per-column operation sequence to the reference's
-// left-looking loop) on a column-major copy, two small launches per column: normalise column j,
-// then project it out of every later column.  BLAS-2 by nature, L2 resident for typical sizes.
+// left-looking loop) on a column-major copy, ONE launch per column: project q_j out of every later
+// column; the CTA that owns column j + 1 also normalises it afterwards (it is final then), so the
+// next launch finds q_{j+1} ready.  BLAS-2 by nature, L2 resident for typical sizes.
 #include "../../include/linalg_b200.h"
 #include "ops.cuh"
 
@@ -48,8 +49,10 @@ __global__ void __launch_bounds__(256) mgs_norm_kernel(double* __restrict__ At, 
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) v[i] = v[i] / nrm;  // true division, qr.py:42
 }
-// columns c > j: r = q_j . a_c ; a_c -= r q_j ; R[j][c] = r      (one CTA per column)
-__global__ void __launch_bounds__(256) mgs_update_kernel(double* __restrict__ At, int m, int n, int j, double* __restrict__ R) {
+// columns c > j: r = q_j . a_c ; a_c -= r q_j ; R[j][c] = r      (one CTA per column).  Column j + 1 is final after
+// its update: its CTA goes on with R[j+1][j+1] = ||v||, q = v / ||v|| (the work of mgs_norm_kernel for the next step).
+__global__ void __launch_bounds__(256) mgs_update_kernel(double* __restrict__ At, int m, int n, int j, double* __restrict__ R,
+                                                         int* __restrict__ info) {
     __shared__ double red[32];
     const int c = j + 1 + blockIdx.x;
     const double* q = At + (size_t)j * m;
@@ -57,8 +60,21 @@ __global__ void __launch_bounds__(256) mgs_update_kernel(double* __restrict__ At
     double p = 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) p = fma(q[i], a[i], p);
     const double r = block_sum256(p, red);
-    for (int i = threadIdx.x; i < m; i += blockDim.x) a[i] = fma(-r, q[i], a[i]);
+    double p2 = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = fma(-r, q[i], a[i]);
+        a[i] = v;
+        p2 = fma(v, v, p2);
+    }
     if (threadIdx.x == 0) R[(size_t)j * n + c] = r;
+    if (blockIdx.x == 0) {
+        const double nrm = sqrt(block_sum256(p2, red));
+        if (threadIdx.x == 0) {
+            R[(size_t)c * n + c] = nrm;
+            if (nrm < kEps && info && *info == 0) *info = c + 1;  // qr.py:40-41
+        }
+        for (int i = threadIdx.x; i < m; i += blockDim.x) a[i] = a[i] / nrm;  // true division, qr.py:42 (own writes)
+    }
 }
 __global__ void __launch_bounds__(256) backsub_cols_kernel(const double* __restrict__ R, int n, double* __restrict__ Y, int k) {
     for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < k; col += gridDim.x * blockDim.x) {
@@ -82,13 +98,11 @@ int large_mgs_qr(Ctx* c, const double* A, int m, int n, int reorth, double* Q, d
     LQ_CUDA(c, cudaMemsetAsync(R, 0, sizeof(double) * (size_t)n * n, c->stream));
     if (info) LQ_CUDA(c, cudaMemsetAsync(info, 0, sizeof(int), c->stream));
     for (int sweep = 0; sweep <= (reorth ? 1 : 0); ++sweep) {
-        for (int j = 0; j < n; ++j) {
-            mgs_norm_kernel<<<1, 256, 0, c->stream>>>(At.as<double>(), m, n, j, R, info);
+        mgs_norm_kernel<<<1, 256, 0, c->stream>>>(At.as<double>(), m, n, 0, R, info);
+        LQ_COUNT_LAUNCH(c);
+        for (int j = 0; j + 1 < n; ++j) {
+            mgs_update_kernel<<<n - 1 - j, 256, 0, c->stream>>>(At.as<double>(), m, n, j, R, info);
             LQ_COUNT_LAUNCH(c);
-            if (j + 1 < n) {
-                mgs_update_kernel<<<n - 1 - j, 256, 0, c->stream>>>(At.as<double>(), m, n, j, R);
-                LQ_COUNT_LAUNCH(c);
-            }
         }
         LQ_CHECK_LAUNCH(c);
     }
