@@ -691,6 +691,20 @@ int blocked_householder_qr(Ctx* c, const double* A, int m, int n, double* Q, dou
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
     const bool skip_q = getenv("LINALG_B200_DEBUG_SKIP_Q") != nullptr;  // timing experiments only (Q = I)
+    // A block reflector transforms every COLUMN of Q independently, so the columns are split into two contiguous
+    // ranges that run the whole chain of applications on two streams with no synchronisation in between: the launch
+    // gaps, split-K reductions and partial last waves of one range are filled by the other.  The split balances the
+    // flops (block b touches the columns >= 128 b only): 3 s^2 - s^3 = 1  ->  s = 0.65.
+    const bool two_ranges = ldq >= 2048 && ws_fits && getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr;
+    const int split = two_ranges ? (int)(0.65 * ldq) / NB_OUT * NB_OUT : 0;
+    cudaStream_t s_main = c->stream, s_side = c->lane[0];
+    EventPool qpool;
+    if (two_ranges) {
+        cudaEvent_t e0;
+        LQ_TRY(qpool.make(c, &e0));
+        LQ_CUDA(c, cudaEventRecord(e0, s_main));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_side, e0, 0));
+    }
     for (int blk = keep.nblocks - 1; blk >= 0 && !skip_q; --blk) {
         const int k0 = blk * NB_OUT;
         const int kb = std::min(NB_OUT, npad - k0);
@@ -699,7 +713,18 @@ int blocked_householder_qr(Ctx* c, const double* A, int m, int n, double* Q, dou
         const double* Vb = Vw.as<double>() + (size_t)k0 * npad + k0;
         const double* Tblk = keep.Tall.as<double>() + (size_t)blk * NB_OUT * NB_OUT;
         // only columns >= k0 of Q are touched by this block (Q[k0:, :k0] is still zero)
-        LQ_TRY(apply_block_reflector(c, Vb, npad, Tblk, NB_OUT, false, mk, kb, Qp + (size_t)k0 * ldq + k0, ldq, ldq - k0, W, W2));
+        const int c_hi = std::max(k0, split);  // main stream: columns [c_hi, ldq); side stream: [k0, split)
+        LQ_TRY(apply_block_reflector(c, Vb, npad, Tblk, NB_OUT, false, mk, kb, Qp + (size_t)k0 * ldq + c_hi, ldq, ldq - c_hi, W, W2));
+        if (k0 < split) {
+            StreamScope side(c, s_side);
+            LQ_TRY(apply_block_reflector(c, Vb, npad, Tblk, NB_OUT, false, mk, kb, Qp + (size_t)k0 * ldq + k0, ldq, split - k0, W, W));
+        }
+    }
+    if (two_ranges) {
+        cudaEvent_t e1;
+        LQ_TRY(qpool.make(c, &e1));
+        LQ_CUDA(c, cudaEventRecord(e1, s_side));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_main, e1, 0));
     }
     if (Qp != Q) {
         unpad_copy_kernel<<<grid_for(c, (long long)m * n), 256, 0, c->stream>>>(Qp, ldq, Q, n, m, n);
