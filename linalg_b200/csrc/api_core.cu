@@ -211,6 +211,7 @@ int lq_create(int device, lq_ctx** out) {
     LQ_CUDA(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     LQ_CUDA(c, cudaStreamCreateWithFlags(&c->lane[0], cudaStreamNonBlocking));
     for (int i = 1; i < 3; ++i) LQ_CUDA(c, cudaStreamCreateWithPriority(&c->lane[i], cudaStreamNonBlocking, prio_hi));
+    LQ_CUDA(c, cudaStreamCreateWithFlags(&c->lane[3], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) LQ_CUDA(c, cudaEventCreate(&c->ev[i]));
     // keep freed scratch cached in the stream-ordered pool
     cudaMemPool_t pool;
@@ -230,7 +231,7 @@ int lq_destroy(lq_ctx* h) {
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
         if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -382,9 +382,9 @@ struct EventPool {
 int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double* V, int ldv, double* B, int ldb,
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
-    cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1], s_merge = c->lane[2];
+    cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1], s_merge = c->lane[2], s_side2 = c->lane[3];
     const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
-    DevBuf Tloc, G, W, W2, Ws, W2s;
+    DevBuf Tloc, G, W, W2, Ws, W2s, W2s2;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
@@ -394,6 +394,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     if (lookahead) {
         LQ_TRY(Ws.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
         LQ_TRY(W2s.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
+        LQ_TRY(W2s2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
         LQ_TRY(Wa.alloc(c, sizeof(double) * NB_IN * (size_t)NB_OUT));
         LQ_TRY(W2a.alloc(c, sizeof(double) * NB_IN * (size_t)NB_OUT));
     }
@@ -415,7 +416,11 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     struct BlockTrace { cudaEvent_t panels = nullptr, chain = nullptr, next = nullptr, rest = nullptr; };
     std::vector<BlockTrace> btrace(trace_blocks ? nblocks : 0);
     cudaEvent_t ev_t0 = nullptr;
-    cudaEvent_t ev_rest_prev = nullptr;  // completion of the side stream's last trailing update
+    cudaEvent_t ev_rest_prev = nullptr;   // completion of the trailing update that held the NEXT block's columns
+    cudaEvent_t ev_rest_last[2] = {nullptr, nullptr};  // last trailing updates of the two column ranges (final join)
+    // the trailing update runs on two independent column ranges (block reflectors act on columns independently), split
+    // where the flops balance (3 s^2 - s^3 = 1): launch gaps, reductions and partial waves of one range are filled by the other
+    const int rsplit = (lookahead && npad >= 6144) ? (int)(0.65 * npad) / NB_OUT * NB_OUT : 0;
     if (trace_blocks) {
         LQ_TRY(pool.make(c, &ev_t0));
         LQ_CUDA(c, cudaEventRecord(ev_t0, s_main));
@@ -428,6 +433,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         LQ_CUDA(c, cudaStreamWaitEvent(s_side, e0, 0));
         LQ_CUDA(c, cudaStreamWaitEvent(s_aux, e0, 0));
         LQ_CUDA(c, cudaStreamWaitEvent(s_merge, e0, 0));
+        LQ_CUDA(c, cudaStreamWaitEvent(s_side2, e0, 0));
     }
     for (int blk = 0; blk < nblocks; ++blk) {
         const int k0 = blk * NB_OUT;
@@ -531,22 +537,40 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             } else {
                 LQ_CUDA(c, cudaEventRecord(ev_after, s_main));  // T merged on the main stream
             }
-            StreamScope side(c, s_side);
-            LQ_CUDA(c, cudaStreamWaitEvent(s_side, ev_after, 0));
-            if (nrest > 0)
-                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr + nnext, lda, nrest,
+            const int c_lo = k0 + kb + nnext;             // first column of the trailing update
+            const int c_mid = std::max(c_lo, std::min(rsplit, npad));
+            cudaEvent_t ev_left = nullptr, ev_right = nullptr;
+            if (c_mid > c_lo) {
+                StreamScope side(c, s_side);  // columns [c_lo, c_mid)
+                LQ_CUDA(c, cudaStreamWaitEvent(s_side, ev_after, 0));
+                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, A + (size_t)k0 * lda + c_lo, lda, c_mid - c_lo,
                                              Ws.as<double>(), W2s.as<double>()));
-            if (B && nrhs_pad > 0)
-                LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
-                                             Ws.as<double>(), W2s.as<double>()));
-            cudaEvent_t ev_rest;
-            LQ_TRY(pool.make(c, &ev_rest));
-            LQ_CUDA(c, cudaEventRecord(ev_rest, s_side));
-            ev_rest_prev = ev_rest;
-            if (trace_blocks) btrace[blk].rest = ev_rest;
+                LQ_TRY(pool.make(c, &ev_left));
+                LQ_CUDA(c, cudaEventRecord(ev_left, s_side));
+                ev_rest_last[0] = ev_left;
+            }
+            {
+                StreamScope side(c, s_side2);  // columns [c_mid, npad) and the right-hand sides
+                LQ_CUDA(c, cudaStreamWaitEvent(s_side2, ev_after, 0));
+                if (npad > c_mid)
+                    LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, A + (size_t)k0 * lda + c_mid, lda, npad - c_mid,
+                                                 Ws.as<double>(), W2s2.as<double>()));
+                if (B && nrhs_pad > 0)
+                    LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, B + (size_t)k0 * ldb, ldb, nrhs_pad,
+                                                 Ws.as<double>(), W2s2.as<double>()));
+                LQ_TRY(pool.make(c, &ev_right));
+                LQ_CUDA(c, cudaEventRecord(ev_right, s_side2));
+                ev_rest_last[1] = ev_right;
+            }
+            // the next block's columns of the NEXT iteration are the first columns of this trailing update
+            ev_rest_prev = ev_left ? ev_left : ev_right;
+            if (trace_blocks) btrace[blk].rest = ev_rest_prev;
         }
     }
-    if (lookahead && ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));  // join
+    if (lookahead) {  // join
+        for (cudaEvent_t e : ev_rest_last)
+            if (e) LQ_CUDA(c, cudaStreamWaitEvent(s_main, e, 0));
+    }
     if (trace_blocks) {
         LQ_CUDA(c, cudaStreamSynchronize(s_main));
         fprintf(stderr, "# blk  panels_done  chain_done  next_done  rest_done   (ms since start; m=%d npad=%d)\n", m, npad);

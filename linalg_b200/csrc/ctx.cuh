@@ -17,8 +17,9 @@ struct Ctx : lq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     // lane 0 / 1: copy-compute lanes of the host-pointer pipelines and side / aux streams of the blocked QR's look-ahead;
-    // lane 2: T-merge stream of the blocked QR.  Lanes 1 and 2 carry latency-critical work: high priority.
-    cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+    // lane 2: T-merge stream of the blocked QR (lanes 1 and 2 carry latency-critical work: high priority);
+    // lane 3: second trailing-update stream of the blocked QR.
+    cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[16] = {};
     cudaDeviceProp prop{};
     int sm_count = 0;
