@@ -426,21 +426,19 @@ __global__ void __launch_bounds__(256) jacobi_apply_kernel(const double2* __rest
     for (int j = threadIdx.x; j < ne; j += blockDim.x) row[j] = (j == b) ? 1.0 : 0.0;
     __syncthreads();
     const int R = *nrounds;
-    // thread k replays rotation k of every round; the (c, s) pair of the next round is fetched while the current
-    // one is applied (the log lives in L2, its latency would otherwise be paid once per round)
-    const int k = threadIdx.x;
-    double2 cur = (k < half && R > 0) ? rotlog[k] : make_double2(1.0, 0.0);
+    // a round's ne / 2 rotations are disjoint: the threads of the CTA share them (any ne / 2, not just <= blockDim.x)
     for (int rd = 0; rd < R; ++rd) {
-        const double2 nxt = (k < half && rd + 1 < R) ? rotlog[(size_t)(rd + 1) * half + k] : make_double2(1.0, 0.0);
-        if (k < half && cur.y != 0.0) {
-            int p, q;
-            rr_pair(ne, rd % (ne - 1), k, p, q);
-            const double vp = row[p], vq = row[q];
-            row[p] = cur.x * vp - cur.y * vq;
-            row[q] = cur.y * vp + cur.x * vq;
+        for (int k = threadIdx.x; k < half; k += blockDim.x) {
+            const double2 cur = rotlog[(size_t)rd * half + k];
+            if (cur.y != 0.0) {
+                int p, q;
+                rr_pair(ne, rd % (ne - 1), k, p, q);
+                const double vp = row[p], vq = row[q];
+                row[p] = cur.x * vp - cur.y * vq;
+                row[q] = cur.y * vp + cur.x * vq;
+            }
         }
         __syncthreads();
-        cur = nxt;
     }
     for (int j = threadIdx.x; j < n; j += blockDim.x) V[(size_t)b * n + j] = row[j];
 }
@@ -837,7 +835,7 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
     jacobi_kernel<<<1, 1024, smem, c->stream>>>(G, n, Aw.as<double>(), use_global, rot.as<double2>(), max_sweeps, rel_tol,
                                                nr.as<int>(), lam.as<double>());
     LQ_CHECK_LAUNCH(c);
-    jacobi_apply_kernel<<<n, 128, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, ne, Vraw.as<double>());
+    jacobi_apply_kernel<<<n, 256, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, ne, Vraw.as<double>());
     LQ_CHECK_LAUNCH(c);
     eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
     LQ_CHECK_LAUNCH(c);

@@ -348,8 +348,16 @@ def test_svd_tall_skinny(ctx):
     assert np.all(np.diff(s) <= 0)
 
 
+def test_svd_more_than_256_columns(ctx):
+    A = np.random.default_rng(77).standard_normal((1500, 300))
+    U, s, Vt = lb.svd(A, ctx=ctx)
+    assert np.max(np.abs(s - np.linalg.svd(A, compute_uv=False)) / s) <= REL
+    assert np.abs(U.T @ U - np.eye(300)).max() <= 1e-10 and np.abs(Vt @ Vt.T - np.eye(300)).max() <= 1e-10
+    assert np.linalg.norm((U * s) @ Vt - A) / np.linalg.norm(A) <= 1e-12
+
+
 def test_eigh_building_block(ctx):
-    for n in (1, 2, 5, 64, 127, 128, 200):
+    for n in (1, 2, 5, 64, 127, 128, 200, 258, 400):  # > 256: more rotations per round than threads in the replay
         M = np.random.default_rng(n).standard_normal((n + 5, n))
         G = M.T @ M
         dG, dl, dV = ctx.upload(G), ctx.alloc(8 * n), ctx.alloc(8 * n * n)
