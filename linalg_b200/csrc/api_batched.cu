@@ -4,6 +4,7 @@
 #include "../../include/linalg_b200.h"
 #include "batched_qr32.cuh"
 #include "batched_qr32_pipe.cuh"
+#include "batched_qr32_dmma.cuh"
 #include "batched_small.cuh"
 #include "ctx.cuh"
 #include "ops.cuh"
@@ -47,6 +48,24 @@ static int launch_hh32_pipe(Ctx* c, cudaStream_t st, const double* A, long long 
     return LQ_OK;
 }
 
+// R phase on DFMA, Q formation as compact-WY block reflectors on the FP64 tensor pipe (DMMA.8x8x4)
+template <int WARPS, int MINB, int PHASES = 3>
+static int launch_hh32_dmma(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
+    auto kern = hh_qr32_dmma_kernel<WARPS, MINB, PHASES>;
+    const size_t smem = (size_t)WARPS * Dmma32::warp_doubles() * sizeof(double);
+    static bool configured[64] = {};
+    if (!configured[c->device]) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device] = true;
+    }
+    const long long per_block = (long long)WARPS * 2;
+    const long long blocks = (batch + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
 template <int P, int C, int WARPS, int MINB>
 static int launch_mgs32(Ctx* c, cudaStream_t st, const double* A, long long batch, int reorth, double* Q, double* R,
                         int* info) {
@@ -81,6 +100,11 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 11: return launch_hh32<2, 2, 4, true, 3>(c, st, A, batch, Q, R);
             case 12: return launch_hh32<4, 4, 2, true, 8, 2>(c, st, A, batch, Q, R);
             case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
+            case 20: return launch_hh32_dmma<2, 4>(c, st, A, batch, Q, R);
+            case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
+            case 22: return launch_hh32_dmma<1, 8>(c, st, A, batch, Q, R);
+            case 23: return launch_hh32_dmma<4, 2, 1>(c, st, A, batch, Q, R);
+            case 24: return launch_hh32_dmma<4, 2, 2>(c, st, A, batch, Q, R);
             default: break;
         }
         set_error(c, "householder_qr_batched: unknown kernel variant %d", variant);
