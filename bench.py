@@ -353,6 +353,25 @@ def main():
     }
     dI.free()
 
+    # ---- cfg2 strong scaling: 2^20 matrices IN TOTAL, batch-sharded over the ranks (no collective); every step is
+    # bracketed by a barrier so launch / barrier overhead shows (1.2 ms kernels at N = 8)
+    sb = PER_GPU_BATCH // info.world
+    if sb <= batch:
+        per = []
+        for i in range(3 + 10):
+            ctx.sync()
+            d.barrier()
+            ctx.record(0)
+            ctx.call("lq_householder_qr_batched_dev", dA.ptr, sb, N32, N32, dQ.ptr, dR.ptr, 0)
+            ctx.record(1)
+            ctx.sync()
+            if i >= 3:
+                per.append(d.max_over_ranks(ctx.elapsed_ms(0, 1)))
+        sms = statistics.mean(per)
+        extras["cfg2_strong_1M_total"] = {"matrices_total": sb * info.world, "matrices_per_gpu": sb, "ms": sms,
+                                          "matrices_per_s": sb * info.world / (sms * 1e-3), "scaling": "strong",
+                                          "hbm_frac_per_gpu": sb * BYTES_PER_MATRIX / (sms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
     # ---- end to end: pinned host buffers through the host-pointer C-ABI call
     e2e_steps = args.e2e_steps or min(args.steps, 5)
     budget = host_memory_budget_bytes() // max(1, info.world)
@@ -387,7 +406,9 @@ def main():
     if not args.no_extras:
         try:
             extras.update(run_extras(ctx, d, info, peaks))
-        except Exception as exc:  # extras must never lose the headline line
+        except ParityError:
+            raise                  # a timed configuration with a wrong result fails the run
+        except Exception as exc:  # anything else in the extras must never lose the headline line
             extras["extras_error"] = repr(exc)
 
     sampler.stop()
@@ -434,6 +455,93 @@ def main():
     return 0
 
 
+# ----------------------------------------------------------------------------- parity of the timed outputs
+class ParityError(RuntimeError):
+    """A timed configuration produced a result outside the north-star tolerances: the run must fail."""
+
+
+def _require(cond, what, value):
+    if not cond:
+        raise ParityError(f"bench parity check failed: {what} = {value}")
+
+
+def _gram_all(ctx, info, dX, m, n):
+    """G = X^T X over ALL row shards: device Gram (+ one ncclAllReduce of n*n doubles), downloaded."""
+    dG = ctx.alloc(8 * n * n)
+    ctx.call("lq_gram_dev", dX.ptr, m, n, dG.ptr)
+    if info.world > 1:
+        ctx.call("lq_comm_allreduce_sum", dG.ptr, n * n)
+    G = ctx.download(dG, (n, n))
+    dG.free()
+    return G
+
+
+def _row_sample(ctx, dX, m, n, rows=4096):
+    """First / middle / last `rows` rows of a device (m, n) array -> host."""
+    rows = min(rows, m)
+    starts = sorted({0, max(0, m // 2 - rows // 2), m - rows})
+    out = np.empty((len(starts) * rows, n))
+    for k, st in enumerate(starts):
+        ctx.call("lq_memcpy_d2h", out[k * rows:].ctypes.data, dX.ptr + 8 * st * n, 8 * rows * n)
+    ctx.sync()
+    idx = np.concatenate([np.arange(st, st + rows) for st in starts])
+    return idx, out
+
+
+def check_cfg5(ctx, d, info, A, dA, dQ, dR, dU, ds, dVt, m, n):
+    """Checked results behind the tall-skinny timings (north star: ||Q^T Q - I|| <= 1e-12, ||A - QR|| / ||A|| <= 1e-12,
+    singular values to 1e-10 relative), valid for any number of row shards:
+      orthogonality over ALL rows     Gram of Q / U on the device, all-reduced             (linalg/qr.py:39-42 convention)
+      residual                        per rank on 3 x 4096 rows of its shard, and over all rows through
+                                      A^T A = R^T R  /  A^T A = V diag(s^2) V^T           (linalg/svd.py:42-64)
+      replication                     R, s, Vt bitwise identical on every rank
+      s(svd route) vs s(R)            np.linalg.svd of the 128 x 128 TSQR factor (host)"""
+    import hashlib
+
+    eye = np.eye(n)
+    out = {}
+    # ---- TSQR
+    R = ctx.download(dR, (n, n))
+    GQ = _gram_all(ctx, info, dQ, m, n)
+    GA = _gram_all(ctx, info, dA, m, n)
+    idx, Qs = _row_sample(ctx, dQ, m, n)
+    As = A[idx]
+    out["tsqr_orth_max"] = float(np.max(np.abs(GQ - eye)))
+    out["tsqr_resid_rows"] = d.max_over_ranks(float(np.linalg.norm(As - Qs @ R) / np.linalg.norm(As)))
+    out["tsqr_gram_resid"] = float(np.linalg.norm(GA - R.T @ R) / np.linalg.norm(GA))
+    out["tsqr_diag_min"] = float(np.min(np.diag(R)))
+    out["tsqr_tril_max"] = float(np.max(np.abs(np.tril(R, -1))))
+    digests = d.allgather_object(hashlib.sha1(R.tobytes()).hexdigest())
+    out["tsqr_R_bitwise_replicated"] = len(set(digests)) == 1
+    _require(out["tsqr_orth_max"] <= 1e-12, "TSQR ||Q^T Q - I||_max", out["tsqr_orth_max"])
+    _require(out["tsqr_resid_rows"] <= 1e-12, "TSQR ||A - Q R|| / ||A|| (row sample, max over ranks)", out["tsqr_resid_rows"])
+    _require(out["tsqr_gram_resid"] <= 1e-12, "TSQR ||A^T A - R^T R|| / ||A^T A||", out["tsqr_gram_resid"])
+    _require(out["tsqr_diag_min"] > 0 and out["tsqr_tril_max"] == 0.0, "TSQR diag(R) > 0, tril(R) == 0", (out["tsqr_diag_min"], out["tsqr_tril_max"]))
+    _require(out["tsqr_R_bitwise_replicated"], "TSQR R identical on every rank", digests)
+    # ---- SVD via the Gram route
+    s, Vt = ctx.download(ds, (n,)), ctx.download(dVt, (n, n))
+    GU = _gram_all(ctx, info, dU, m, n)
+    idx, Us = _row_sample(ctx, dU, m, n)
+    As = A[idx]
+    sR = np.linalg.svd(R, compute_uv=False)
+    out["svd_U_orth_max"] = float(np.max(np.abs(GU - eye)))
+    out["svd_V_orth_max"] = float(np.max(np.abs(Vt @ Vt.T - eye)))
+    out["svd_resid_rows"] = d.max_over_ranks(float(np.linalg.norm(As - (Us * s) @ Vt) / np.linalg.norm(As)))
+    out["svd_gram_resid"] = float(np.linalg.norm(GA - (Vt.T * s ** 2) @ Vt) / np.linalg.norm(GA))
+    out["svd_s_vs_tsqr_R_rel"] = float(np.max(np.abs(s - sR) / sR))
+    out["svd_s_descending"] = bool(np.all(np.diff(s) <= 0))
+    digests = d.allgather_object(hashlib.sha1(s.tobytes() + Vt.tobytes()).hexdigest())
+    out["svd_sVt_bitwise_replicated"] = len(set(digests)) == 1
+    _require(out["svd_U_orth_max"] <= 1e-12, "SVD ||U^T U - I||_max", out["svd_U_orth_max"])
+    _require(out["svd_V_orth_max"] <= 1e-12, "SVD ||V^T V - I||_max", out["svd_V_orth_max"])
+    _require(out["svd_resid_rows"] <= 1e-12, "SVD ||A - U S V^T|| / ||A|| (row sample, max over ranks)", out["svd_resid_rows"])
+    _require(out["svd_gram_resid"] <= 1e-12, "SVD ||A^T A - V S^2 V^T|| / ||A^T A||", out["svd_gram_resid"])
+    _require(out["svd_s_vs_tsqr_R_rel"] <= 1e-10, "singular values: A^T A route vs np.linalg.svd(R_tsqr), relative", out["svd_s_vs_tsqr_R_rel"])
+    _require(out["svd_s_descending"] and out["svd_sVt_bitwise_replicated"], "s descending / (s, Vt) identical on every rank", digests)
+    out["tolerances"] = "orth <= 1e-12, residual <= 1e-12, singular values <= 1e-10 relative (BASELINE.json north_star)"
+    return out
+
+
 # ----------------------------------------------------------------------------- secondary configs
 def run_extras(ctx, d, info, peaks):
     import linalg_b200 as lb  # noqa: F401
@@ -451,16 +559,38 @@ def run_extras(ctx, d, info, peaks):
     B = np.random.default_rng(4 + info.rank).standard_normal((uniq, m, k))
     dA, dB = tile_to_device(ctx, A, nsys // uniq), tile_to_device(ctx, B, nsys // uniq)
     dX = ctx.alloc(8 * nsys * n * k)
+
+    def check_lstsq(tag):
+        # the LAST `uniq` systems of the timed batch against LAPACK (np.linalg.lstsq), 1e-10 relative per system
+        # (north star: least-squares results to 1e-10), plus the normal equations A^T (A x - b) = 0
+        nchk = 256
+        X = np.empty((nchk, n, k))
+        ctx.call("lq_memcpy_d2h", X.ctypes.data, dX.ptr + 8 * (nsys - nchk) * n * k, X.nbytes)
+        ctx.sync()
+        worst, worst_ne = 0.0, 0.0
+        for i in range(nchk):
+            Ai, Bi = A[uniq - nchk + i], B[uniq - nchk + i]
+            Xo = np.linalg.lstsq(Ai, Bi, rcond=None)[0]
+            worst = max(worst, float(np.max(np.abs(X[i] - Xo)) / np.max(np.abs(Xo))))
+            worst_ne = max(worst_ne, float(np.linalg.norm(Ai.T @ (Ai @ X[i] - Bi)) / (np.linalg.norm(Ai) ** 2 * np.linalg.norm(X[i]))))
+        _require(worst <= 1e-10, f"{tag}: max relative error vs np.linalg.lstsq over {nchk} systems", worst)
+        _require(worst_ne <= 1e-13, f"{tag}: normal-equations residual", worst_ne)
+        return {"systems_checked": nchk, "max_rel_err_vs_lapack": worst, "normal_eq_resid": worst_ne}
+
     ms = timed(ctx, lambda: ctx.call("lq_lstsq_householder_batched_dev", dA.ptr, dB.ptr, nsys, m, n, k, dX.ptr), 5, 3)
     t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
     flops = 2905429.0
     out["cfg3_lstsq_hh_256x64x16"] = {
         "systems_per_s": info.world * nsys / t, "ms": t * 1e3, "gflops": info.world * nsys * flops / t / 1e9,
-        "fp64_frac": nsys * flops / t / 1e12 / peak64, "hbm_frac": nsys * 172032 / t / 1e9 / peaks["hbm_gbs"]}
+        "fp64_frac": nsys * flops / t / 1e12 / peak64, "hbm_frac": nsys * 172032 / t / 1e9 / peaks["hbm_gbs"],
+        "parity": check_lstsq("cfg3 householder least squares")}
     dI = ctx.alloc(4 * nsys)
+    ctx.call("lq_memset", dX.ptr, 0, 8 * nsys * n * k)
     ms = timed(ctx, lambda: ctx.call("lq_lstsq_mgs_batched_dev", dA.ptr, dB.ptr, nsys, m, n, k, dX.ptr, dI.ptr), 3, 2)
     t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
-    out["cfg3_lstsq_mgs_256x64x16"] = {"systems_per_s": info.world * nsys / t, "ms": t * 1e3}
+    out["cfg3_lstsq_mgs_256x64x16"] = {"systems_per_s": info.world * nsys / t, "ms": t * 1e3,
+                                       "fp64_frac": nsys * flops / t / 1e12 / peak64,
+                                       "parity": check_lstsq("cfg3 MGS least squares")}
     for b in (dA, dB, dX, dI):
         b.free()
 
@@ -473,31 +603,52 @@ def run_extras(ctx, d, info, peaks):
         lpc = (ctx.launches() - l0) // (reps + 2)
         t = min(ms) * 1e-3
         fqr = 8.0 / 3.0 * nn ** 3
+        # checked result: randomised invariants in O(n^2) host work (8 probe vectors) + exact structure of R
+        Qh, Rh = ctx.download(dQ, (nn, nn)), ctx.download(dR, (nn, nn))
+        Xp = np.random.default_rng(50).standard_normal((nn, 8))
+        resid = float(np.linalg.norm(A @ Xp - Qh @ (Rh @ Xp)) / (np.linalg.norm(A) * np.linalg.norm(Xp) / np.sqrt(nn)))
+        orth = float(np.linalg.norm(Qh.T @ (Qh @ Xp) - Xp) / np.linalg.norm(Xp))
+        tril = float(np.max(np.abs(np.tril(Rh, -1))))
+        # sign convention of linalg/qr.py:82-86: R[j, j] = -copysign(||x||, x0); for column 0, x0 = A[0, 0]
+        sign0 = bool(np.sign(Rh[0, 0]) == -np.sign(A[0, 0])) and abs(abs(Rh[0, 0]) - np.linalg.norm(A[:, 0])) <= 1e-12 * np.linalg.norm(A[:, 0])
+        _require(resid <= 1e-12 and orth <= 1e-12 and tril == 0.0 and sign0, f"blocked householder_qr {nn}^2 (resid, orth, tril, sign)", (resid, orth, tril, sign0))
         out[f"blocked_hh_{nn}"] = {"ms_best": t * 1e3, "ms_mean": statistics.mean(ms), "tflops_FQR": fqr / t / 1e12,
-                                   "fp64_frac": fqr / t / 1e12 / peak64, "launches_per_call": int(lpc), "replicas": info.world}
+                                   "fp64_frac": fqr / t / 1e12 / peak64, "launches_per_call": int(lpc), "replicas": info.world,
+                                   "parity": {"probe_resid": resid, "probe_orth": orth, "tril_max": tril, "r00_sign_and_norm": sign0}}
+        del Qh, Rh
         for b in (dA, dQ, dR):
             b.free()
 
-    # ---- cfg5: tall-skinny 2^20 x 128 rows per GPU, row-sharded with NCCL when N > 1
-    m, n = 1 << 20, 128
+    # ---- cfg5: tall-skinny 2^20 x 128 rows per GPU, row-sharded with NCCL when N > 1 (weak), then 2^23 rows in total (strong)
+    n = 128
     if info.world > 1:
         d.init_comm(ctx, info)
-    A = np.random.default_rng(6 + 1000 * info.rank).standard_normal((m, n))
-    dA, dU, dR = ctx.upload(A), ctx.alloc(A.nbytes), ctx.alloc(8 * n * n)
-    ds, dVt = ctx.alloc(8 * n), ctx.alloc(8 * n * n)
-    rk = C.c_int(0)
     sh = "_sharded" if info.world > 1 else ""
-    ms = timed(ctx, lambda: ctx.call("lq_svd_gram" + sh + "_dev", dA.ptr, m, n, C.c_double(1e-12), dU.ptr, ds.ptr, dVt.ptr, C.byref(rk)), 5, 2)
-    t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
-    out["cfg5_svd_gram"] = {"rows_total": m * info.world, "ms": t * 1e3, "gflops": info.world * 2 * 3.44e10 / t / 1e9,
-                            "fp64_frac": 2 * 3.44e10 / t / 1e12 / peak64, "rank": rk.value, "collective": "ncclAllReduce 128x128 f64" if info.world > 1 else None}
-    ms = timed(ctx, lambda: ctx.call("lq_tsqr" + sh + "_dev", dA.ptr, m, n, dU.ptr, dR.ptr), 5, 2)
-    t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
-    executed = 4 * 2.0 * m * n * n  # CholeskyQR2: two Gram products + two triangular-inverse products
-    out["cfg5_tsqr"] = {"rows_total": m * info.world, "ms": t * 1e3, "gflops_householder_equiv": info.world * 6.9e10 / t / 1e9,
-                        "executed_tflops_per_gpu": executed / t / 1e12, "fp64_frac": executed / t / 1e12 / peak64,
-                        "hbm_frac": 2.147e9 / t / 1e9 / peaks["hbm_gbs"],
-                        "collective": "2 x ncclAllReduce 128x128 f64 (Gram matrices)" if info.world > 1 else None}
+    for tag, m in (("", 1 << 20), ("_strong_8Mx128", (1 << 23) // info.world)):
+        A = np.random.default_rng(6 + 1000 * info.rank).standard_normal((m, n))
+        dA, dU, dQ, dR = ctx.upload(A), ctx.alloc(A.nbytes), ctx.alloc(A.nbytes), ctx.alloc(8 * n * n)
+        ds, dVt = ctx.alloc(8 * n), ctx.alloc(8 * n * n)
+        rk = C.c_int(0)
+        ms = timed(ctx, lambda: ctx.call("lq_svd_gram" + sh + "_dev", dA.ptr, m, n, C.c_double(1e-12), dU.ptr, ds.ptr, dVt.ptr, C.byref(rk)), 5, 2)
+        t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
+        f_svd = 2.0 * 2.0 * m * n * n      # Gram (full GEMM count) + U = A V S^-1
+        out["cfg5_svd_gram" + tag] = {"rows_total": m * info.world, "rows_per_gpu": m, "ms": t * 1e3, "gflops": info.world * f_svd / t / 1e9,
+                                      "fp64_frac": f_svd / t / 1e12 / peak64, "rank": rk.value,
+                                      "collective": "ncclAllReduce 128x128 f64" if info.world > 1 else None}
+        ms = timed(ctx, lambda: ctx.call("lq_tsqr" + sh + "_dev", dA.ptr, m, n, dQ.ptr, dR.ptr), 5, 2)
+        t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
+        executed = 4 * 2.0 * m * n * n  # CholeskyQR2: two Gram products + two triangular-inverse products
+        algorithmic = 4.0 * m * n * n   # Householder-equivalent: factor (2 m n^2) + explicit Q (2 m n^2)
+        out["cfg5_tsqr" + tag] = {"rows_total": m * info.world, "rows_per_gpu": m, "ms": t * 1e3,
+                                  "gflops_householder_equiv": info.world * algorithmic / t / 1e9,
+                                  "fp64_frac_algorithmic": algorithmic / t / 1e12 / peak64,
+                                  "executed_tflops_per_gpu": executed / t / 1e12, "fp64_frac_executed": executed / t / 1e12 / peak64,
+                                  "hbm_frac": 2.0 * A.nbytes / t / 1e9 / peaks["hbm_gbs"],
+                                  "collective": "2 x ncclAllReduce 128x128 f64 (Gram matrices)" if info.world > 1 else None}
+        out["cfg5_parity" + tag] = check_cfg5(ctx, d, info, A, dA, dQ, dR, dU, ds, dVt, m, n)
+        for b in (dA, dU, dQ, dR, ds, dVt):
+            b.free()
+        del A
     return out
 
 

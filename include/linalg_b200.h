@@ -57,6 +57,11 @@ int lq_event_elapsed_ms(lq_ctx* ctx, int slot_a, int slot_b, float* ms); /* sync
 int lq_flush_l2(lq_ctx* ctx);        /* overwrite a 256 MiB scratch buffer (> 126 MB L2) */
 int64_t lq_kernel_launches(lq_ctx* ctx); /* number of this library's kernels launched so far */
 
+/* diagnostics: kernel-selection switches of one context.  name is the LINALG_B200_<NAME> environment variable without
+ * its prefix ("TSQR_HOUSEHOLDER", "JACOBI_TWO_SIDED", "OLD_CHOL"); the environment only gives the initial value at
+ * lq_create, hot entry points never call getenv. */
+int lq_set_option(lq_ctx* ctx, const char* name, int value);
+
 /* ---- a1: householder_qr  (linalg/qr.py:52-100) ------------------------------------------- */
 /* A (batch, m, n) -> Q (batch, m, n), R (batch, n, n); requires m >= n >= 1.
  * variant: 0 = library default; other values select a specific kernel (bench/tests). */

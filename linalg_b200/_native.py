@@ -28,6 +28,7 @@ SIGNATURES = {
     "lq_create": (C.c_int, [C.c_int, c_void_pp]),
     "lq_destroy": (C.c_int, [_CTX]),
     "lq_last_error": (C.c_char_p, [_CTX]),
+    "lq_set_option": (C.c_int, [_CTX, C.c_char_p, C.c_int]),
     "lq_device_props": (C.c_int, [_CTX, C.POINTER(C.c_int64)]),
     "lq_malloc": (C.c_int, [_CTX, C.c_size_t, c_void_pp]),
     "lq_free": (C.c_int, [_CTX, C.c_void_p]),
@@ -173,6 +174,10 @@ class Context:
     def call(self, name: str, *args):
         rc = getattr(self.lib, name)(self.handle, *args)
         check(self.lib, self.handle, rc, name)
+
+    def set_option(self, name: str, value: bool):
+        """Diagnostic kernel-selection switch (``TSQR_HOUSEHOLDER``, ``JACOBI_TWO_SIDED``, ``OLD_CHOL``)."""
+        self.call("lq_set_option", name.encode(), int(bool(value)))
 
     def props(self):
         arr = (C.c_int64 * 8)()

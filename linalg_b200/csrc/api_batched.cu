@@ -5,6 +5,8 @@
 #include "batched_qr32.cuh"
 #include "batched_qr32_pipe.cuh"
 #include "batched_qr32_dmma.cuh"
+#include "batched_qr32_ll.cuh"
+#include "batched_qr32_c8.cuh"
 #include "batched_small.cuh"
 #include "ctx.cuh"
 #include "ops.cuh"
@@ -17,10 +19,10 @@ static int launch_hh32(Ctx* c, cudaStream_t st, const double* A, long long batch
     using D = Dist32<P, C>;
     auto kern = hh_qr32_kernel<P, C, WARPS, KEEPV, MINB, NR>;
     const size_t smem = (size_t)WARPS * D::MPW * D::SMEM_DOUBLES * sizeof(double);
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     const long long per_block = (long long)WARPS * D::MPW;
     const long long blocks = (batch + per_block - 1) / per_block;
@@ -35,10 +37,10 @@ template <int WARPS, int MINB, int NR>
 static int launch_hh32_pipe(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
     auto kern = hh_qr32_pipe_kernel<WARPS, MINB, NR>;
     const size_t smem = (size_t)WARPS * Pipe32::WARP_DOUBLES * sizeof(double);
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     const long long pairs = (batch + 1) / 2;
     const long long blocks = std::min<long long>((long long)c->sm_count * MINB, (pairs + WARPS - 1) / WARPS);
@@ -53,12 +55,48 @@ template <int WARPS, int MINB, int PHASES = 3>
 static int launch_hh32_dmma(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
     auto kern = hh_qr32_dmma_kernel<WARPS, MINB, PHASES>;
     const size_t smem = (size_t)WARPS * Dmma32::warp_doubles() * sizeof(double);
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     const long long per_block = (long long)WARPS * 2;
+    const long long blocks = (batch + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+// register-light left-looking R phase (NS column stages, packed reflectors) + DMMA Q phase
+template <int NS, int WARPS, int MINB, int PHASES = 3, bool KEEPV = false>
+static int launch_hh32_ll(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
+    auto kern = hh_qr32_ll_kernel<NS, WARPS, MINB, PHASES, KEEPV>;
+    const size_t smem = (size_t)WARPS * Pack32::WARP_DOUBLES * sizeof(double);
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set(c->device);
+    }
+    const long long per_block = (long long)WARPS * 2;
+    const long long blocks = (batch + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
+// lane = column, four matrices per warp, left-looking panels + DMMA Q phase
+template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false>
+static int launch_hh32_c8(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
+    auto kern = hh_qr32_c8_kernel<WARPS, MINB, PHASES, KEEPV>;
+    const size_t smem = (size_t)WARPS * Col8::WARP_DOUBLES * sizeof(double);
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set(c->device);
+    }
+    const long long per_block = (long long)WARPS * 4;
     const long long blocks = (batch + per_block - 1) / per_block;
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, batch);
     LQ_CHECK_LAUNCH(c);
@@ -85,8 +123,9 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
     if (batch == 0) return LQ_OK;
     if (m == 32 && n == 32 && variant >= 0) {
         switch (variant) {
-            case 0:
-            case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // default: reciprocal seeded from the raw rsqrt
+            case 0:   // default (round 2): lane = column, left-looking panels, Q formation on DMMA, one 8-warp CTA per SM
+            case 59: return launch_hh32_c8<8, 1, 3, true>(c, st, A, batch, Q, R);
+            case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // round-1 default: reciprocal seeded from the raw rsqrt
             case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
             case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
@@ -104,6 +143,28 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
             case 22: return launch_hh32_dmma<1, 8>(c, st, A, batch, Q, R);
             case 23: return launch_hh32_dmma<4, 2, 1>(c, st, A, batch, Q, R);
+            case 50: return launch_hh32_c8<2, 5>(c, st, A, batch, Q, R);
+            case 51: return launch_hh32_c8<2, 4>(c, st, A, batch, Q, R);
+            case 52: return launch_hh32_c8<4, 2>(c, st, A, batch, Q, R);
+            case 53: return launch_hh32_c8<2, 5, 1>(c, st, A, batch, Q, R);
+            case 54: return launch_hh32_c8<2, 5, 2>(c, st, A, batch, Q, R);
+            case 55: return launch_hh32_c8<2, 5, 3, true>(c, st, A, batch, Q, R);
+            case 56: return launch_hh32_c8<2, 4, 3, true>(c, st, A, batch, Q, R);
+            case 57: return launch_hh32_c8<2, 5, 1, true>(c, st, A, batch, Q, R);
+            case 58: return launch_hh32_c8<4, 2, 3, true>(c, st, A, batch, Q, R);
+            case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
+            case 61: return launch_hh32_c8<4, 2, 1, true>(c, st, A, batch, Q, R);
+            case 62: return launch_hh32_c8<4, 2, 1, false>(c, st, A, batch, Q, R);
+            case 63: return launch_hh32_c8<4, 2, 2, false>(c, st, A, batch, Q, R);
+            case 30: return launch_hh32_ll<2, 4, 4>(c, st, A, batch, Q, R);
+            case 32: return launch_hh32_ll<2, 4, 4, 1>(c, st, A, batch, Q, R);
+            case 34: return launch_hh32_ll<2, 4, 3>(c, st, A, batch, Q, R);
+            case 36: return launch_hh32_ll<2, 4, 3, 3, true>(c, st, A, batch, Q, R);
+            case 37: return launch_hh32_ll<2, 4, 3, 1, true>(c, st, A, batch, Q, R);
+            case 38: return launch_hh32_ll<1, 4, 2, 3, true>(c, st, A, batch, Q, R);
+            case 39: return launch_hh32_ll<1, 4, 2, 1, true>(c, st, A, batch, Q, R);
+            case 40: return launch_hh32_ll<2, 4, 4, 2>(c, st, A, batch, Q, R);
+            case 41: return launch_hh32_ll<2, 2, 6, 3, true>(c, st, A, batch, Q, R);
             case 24: return launch_hh32_dmma<4, 2, 2>(c, st, A, batch, Q, R);
             default: break;
         }
@@ -112,10 +173,10 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
     }
     const size_t smem = small_hh_smem_doubles(m, n, 0) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
-        static bool configured[64] = {};
-        if (!configured[c->device]) {
+        static DeviceLatch configured;
+        if (!configured.test(c->device)) {
             LQ_CUDA(c, cudaFuncSetAttribute(small_hh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-            configured[c->device] = true;
+            configured.set(c->device);
         }
         small_hh_kernel<0><<<(unsigned)batch, 256, smem, st>>>(A, nullptr, Q, R, nullptr, m, n, 0);
         LQ_CHECK_LAUNCH(c);
@@ -138,10 +199,10 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
     }
     const size_t smem = small_mgs_smem_doubles(m, n, 0) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
-        static bool configured[64] = {};
-        if (!configured[c->device]) {
+        static DeviceLatch configured;
+        if (!configured.test(c->device)) {
             LQ_CUDA(c, cudaFuncSetAttribute(small_mgs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-            configured[c->device] = true;
+            configured.set(c->device);
         }
         small_mgs_kernel<0><<<(unsigned)batch, 256, smem, st>>>(A, nullptr, Q, R, nullptr, info, m, n, 0, reorth);
         LQ_CHECK_LAUNCH(c);
@@ -161,10 +222,10 @@ int lstsq_hh_batched_stream(Ctx* c, cudaStream_t st, const double* A, const doub
     if (rc != LQ_ERR_UNSUPPORTED) return rc;
     const size_t smem = small_hh_smem_doubles(m, n, nrhs) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
-        static bool configured[64] = {};
-        if (!configured[c->device]) {
+        static DeviceLatch configured;
+        if (!configured.test(c->device)) {
             LQ_CUDA(c, cudaFuncSetAttribute(small_hh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-            configured[c->device] = true;
+            configured.set(c->device);
         }
         small_hh_kernel<1><<<(unsigned)batch, 256, smem, st>>>(A, B, nullptr, nullptr, X, m, n, nrhs);
         LQ_CHECK_LAUNCH(c);
@@ -182,10 +243,10 @@ int lstsq_mgs_batched_stream(Ctx* c, cudaStream_t st, const double* A, const dou
     if (batch == 0) return LQ_OK;
     const size_t smem = small_mgs_smem_doubles(m, n, nrhs) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
-        static bool configured[64] = {};
-        if (!configured[c->device]) {
+        static DeviceLatch configured;
+        if (!configured.test(c->device)) {
             LQ_CUDA(c, cudaFuncSetAttribute(small_mgs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-            configured[c->device] = true;
+            configured.set(c->device);
         }
         small_mgs_kernel<1><<<(unsigned)batch, 256, smem, st>>>(A, B, nullptr, nullptr, X, info, m, n, nrhs, 0);
         LQ_CHECK_LAUNCH(c);

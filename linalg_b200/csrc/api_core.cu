@@ -192,14 +192,24 @@ int lq_create(int device, lq_ctx** out) {
         set_error(nullptr, "device %d out of range [0, %d)", device, n);
         return LQ_ERR_ARG;
     }
-    Ctx* c = new Ctx();
+    // owns the context until every resource exists: a failing CUDA call below returns through lq_destroy
+    struct Guard {
+        Ctx* c;
+        ~Guard() {
+            if (c) {
+                std::string keep = c->err;
+                lq_destroy(c);
+                if (!keep.empty()) global_error() = keep;
+            }
+        }
+    } guard{new Ctx()};
+    Ctx* c = guard.c;
     c->device = device;
     LQ_CUDA(c, cudaSetDevice(device));
     LQ_CUDA(c, cudaGetDeviceProperties(&c->prop, device));
     if (c->prop.major < 10) {
         set_error(nullptr, "device %d is sm_%d%d; linalg_b200 is built for sm_100a only", device, c->prop.major,
                   c->prop.minor);
-        delete c;
         return LQ_ERR_UNSUPPORTED;
     }
     c->sm_count = c->prop.multiProcessorCount;
@@ -218,6 +228,10 @@ int lq_create(int device, lq_ctx** out) {
     LQ_CUDA(c, cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long thr = ~0ull;
     LQ_CUDA(c, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c->env_old_chol = getenv("LINALG_B200_OLD_CHOL") != nullptr;
+    c->env_tsqr_householder = getenv("LINALG_B200_TSQR_HOUSEHOLDER") != nullptr;
+    c->env_jacobi_two_sided = getenv("LINALG_B200_JACOBI_TWO_SIDED") != nullptr;
+    guard.c = nullptr;
     *out = c;
     return LQ_OK;
 }
@@ -235,6 +249,20 @@ int lq_destroy(lq_ctx* h) {
         if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return LQ_OK;
+}
+
+int lq_set_option(lq_ctx* h, const char* name, int value) {
+    Ctx* c = as_ctx(h);
+    if (!c || !name) return LQ_ERR_ARG;
+    const std::string n(name);
+    if (n == "OLD_CHOL") c->env_old_chol = value != 0;
+    else if (n == "TSQR_HOUSEHOLDER") c->env_tsqr_householder = value != 0;
+    else if (n == "JACOBI_TWO_SIDED") c->env_jacobi_two_sided = value != 0;
+    else {
+        set_error(c, "lq_set_option: unknown option '%s'", name);
+        return LQ_ERR_ARG;
+    }
     return LQ_OK;
 }
 
@@ -331,6 +359,7 @@ int lq_event_elapsed_ms(lq_ctx* h, int a, int b, float* ms) {
 int lq_flush_l2(lq_ctx* h) {
     Ctx* c = as_ctx(h);
     if (!c) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
     const size_t bytes = (size_t)256 << 20;
     if (!c->flush_buf) LQ_CUDA(c, cudaMalloc(&c->flush_buf, bytes));
     fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((double*)c->flush_buf, bytes / 8, 1.0);
@@ -345,6 +374,7 @@ int64_t lq_kernel_launches(lq_ctx* h) {
 int lq_probe(lq_ctx* h, int kind, double* result) {
     Ctx* c = as_ctx(h);
     if (!c || !result) return LQ_ERR_ARG;
+    LQ_CUDA(c, cudaSetDevice(c->device));
     cudaEvent_t e0 = c->ev[14], e1 = c->ev[15];
     float ms = 0, best = 1e30f;
     if (kind == 0 || kind == 1 || kind == 3) {

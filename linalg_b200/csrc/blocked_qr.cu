@@ -649,10 +649,10 @@ int back_substitute(Ctx* c, const double* R, int ldr, double* Y, int ldy, int n,
         LQ_COUNT_LAUNCH(c);
         return LQ_OK;
     }
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(backsub_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACKSUB_SMEM));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     const int nblk = (n + 127) / 128;
     for (int b = nblk - 1; b >= 0; --b) {

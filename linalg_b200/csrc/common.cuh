@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -53,6 +54,17 @@ void set_error(Ctx* c, const char* fmt, ...);
         int _rc = (expr);                                                                   \
         if (_rc != 0) return _rc;                                                           \
     } while (0)
+
+// Per-device "this kernel's attributes are set" latch.  Two host threads (two contexts) may race to the first launch:
+// both then set the (idempotent) attribute and both publish the flag -- no torn state, no lock on the hot path.
+// Devices beyond the table are simply configured on every call.
+struct DeviceLatch {
+    std::atomic<unsigned char> f[64];
+    bool test(int d) const { return d >= 0 && d < 64 && f[d].load(std::memory_order_acquire) != 0; }
+    void set(int d) {
+        if (d >= 0 && d < 64) f[d].store(1, std::memory_order_release);
+    }
+};
 
 // ------------------------------------------------------------------ device math helpers
 __device__ __forceinline__ double rcp_seed(double x) {

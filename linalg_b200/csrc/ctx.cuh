@@ -31,6 +31,9 @@ struct Ctx : lq_ctx {
     // NCCL (loaded lazily with dlopen)
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // diagnostic kernel-selection switches: initialised from LINALG_B200_<NAME> when the context is created, changed with
+    // lq_set_option (never read from the environment on a hot entry point)
+    bool env_old_chol = false, env_tsqr_householder = false, env_jacobi_two_sided = false;
 };
 
 std::string& global_error();

@@ -8,6 +8,8 @@
 // Generic path: plain 32x32 tiled kernel for shapes/alignments the fast path does not take.
 #include <cuda.h>  // CUtensorMap types only; the encoder is resolved through cudaGetDriverEntryPoint (no -lcuda)
 
+#include <algorithm>
+
 #include "../../include/linalg_b200.h"
 #include "ops.cuh"
 
@@ -421,11 +423,11 @@ int launch_fast(Ctx* c, long long M, int N, int Kmain, double alpha, const doubl
                 double beta, double* C, int ldc, Partials* parts = nullptr) {
     const bool skinny = AT && !BT && (M <= 64 || N <= 96);
     auto kern = skinny ? gemm_dmma_kernel<AT, BT, AT && !BT> : gemm_dmma_kernel<AT, BT, false>;
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_dmma_kernel<AT, BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_dmma_kernel<AT, BT, AT && !BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     const long long tm = (M + BM - 1) / BM;
     const int tn = (N + BN - 1) / BN;
@@ -791,11 +793,11 @@ int gemm_rank(Ctx* c, long long M, int N, int K, double alpha, const double* A, 
     // measured on B200: the B-stationary walk wins on tall-skinny products (30.2 vs 27.8 TFLOP/s at 2^20 x 128 x 128),
     // the A-stationary walk does not beat the generic kernel on square block updates (23.6 vs 25.0) -> opt-in only
     if (astat && !getenv("LINALG_B200_RANK_ASTAT")) return LQ_ERR_UNSUPPORTED;
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_SMEM_ASTAT));
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_SMEM_BSTAT));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     CUtensorMap mapA;
     LQ_TRY(make_kmajor_map(c, &mapA, A, M, K, lda));
@@ -971,10 +973,10 @@ int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A
     const long long tm = (M + BM - 1) / BM;
     const int tn = (N + UBN - 1) / UBN;
     if (tm * tn < 2LL * c->sm_count) return LQ_ERR_UNSUPPORTED;  // small outputs: the split-K / one-tile paths
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     CUtensorMap mapA;
     LQ_TRY(make_kmajor_map(c, &mapA, A, M, K, lda));
@@ -990,6 +992,16 @@ int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A
 int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, const double* A, int lda, const double* B,
          int ldb, double beta, double* C, int ldc) {
     if (M <= 0 || N <= 0) return LQ_OK;
+    // the kernels index the row tiles with blockIdx.y (<= 65535): very tall products (2^23 x 128 on one GPU) go in row chunks
+    constexpr long long ROW_CHUNK = 1LL << 21;  // 65536 generic 32-row tiles
+    if (M > ROW_CHUNK) {
+        for (long long r = 0; r < M; r += ROW_CHUNK) {
+            const long long mc = std::min(ROW_CHUNK, M - r);
+            const double* Ar = ta ? A + r : A + r * (long long)lda;  // op(A) row r: column r of a transposed A
+            LQ_TRY(gemm(c, ta, tb, mc, N, K, alpha, Ar, lda, B, ldb, beta, C + r * (long long)ldc, ldc));
+        }
+        return LQ_OK;
+    }
     if (K <= 0) {
         // C = beta * C
         if (beta == 1.0) return LQ_OK;
@@ -1064,11 +1076,11 @@ int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, c
 int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int kb, int nc, const double* T, int ldt,
                bool trans_t, double* W2) {
     const size_t rat_smem = ((size_t)kb * (kb + 1) + (size_t)kb * 33 + 8) * sizeof(double);
-    static bool rat_configured[64] = {};
-    if (!rat_configured[c->device]) {
+    static DeviceLatch rat_configured;
+    if (!rat_configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(reduce_apply_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((128 * 129 + 128 * 33 + 8) * sizeof(double))));
-        rat_configured[c->device] = true;
+        rat_configured.set(c->device);
     }
     reduce_apply_t_kernel<<<(nc + 31) / 32, 1024, rat_smem, c->stream>>>(partials, splits, stride, kb, nc, T, ldt,
                                                                        trans_t ? 1 : 0, W2);

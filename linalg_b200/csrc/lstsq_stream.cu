@@ -16,10 +16,10 @@ static int launch_variant(Ctx* c, cudaStream_t st, const double* A, const double
     using Cfg = StreamCfg<3, RPT, WARPS>;
     auto kern = lstsq_stream_kernel<RPT, WARPS>;
     const size_t smem = Cfg::smem_doubles(n) * sizeof(double);
-    static bool configured[64] = {};
-    if (!configured[c->device]) {
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-        configured[c->device] = true;
+        configured.set(c->device);
     }
     kern<<<(unsigned)batch, WARPS * 32, smem, st>>>(A, B, X, m, n, nrhs);
     LQ_CHECK_LAUNCH(c);

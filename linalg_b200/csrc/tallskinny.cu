@@ -709,10 +709,10 @@ __global__ void __launch_bounds__(1024) chol_upper128_kernel(const double* __res
 
 int launch_triu_inverse(Ctx* c, const double* R, int n, double* Rinv) {
     if (n <= 128) {
-        static bool configured[64] = {};
-        if (!configured[c->device]) {
+        static DeviceLatch configured;
+        if (!configured.test(c->device)) {
             LQ_CUDA(c, cudaFuncSetAttribute(triu_inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
-            configured[c->device] = true;
+            configured.set(c->device);
         }
         triu_inverse128_kernel<<<1, 1024, 128 * 129 * 8, c->stream>>>(R, n, Rinv);
     } else {
@@ -731,8 +731,8 @@ __global__ void __launch_bounds__(256) scale_cols_tall_kernel(double* __restrict
 }
 
 int eigh_configure(Ctx* c) {
-    static bool done[64] = {};
-    if (done[c->device]) return LQ_OK;
+    static DeviceLatch done;
+    if (done.test(c->device)) return LQ_OK;
     LQ_CUDA(c, cudaFuncSetAttribute(chol_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
     cudaFuncAttributes fa{};
     LQ_CUDA(c, cudaFuncGetAttributes(&fa, jacobi_kernel));
@@ -743,7 +743,7 @@ int eigh_configure(Ctx* c) {
     LQ_CUDA(c, cudaFuncGetAttributes(&fa, tsqr_leaf_kernel<16, 8>));
     LQ_CUDA(c, cudaFuncSetAttribute(tsqr_leaf_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     c->max_smem - (int)fa.sharedSizeBytes));
-    done[c->device] = true;
+    done.set(c->device);
     return LQ_OK;
 }
 
@@ -798,12 +798,13 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
     // a pair is rotated while |a_pq| > rel_tol * sqrt(a_pp a_qq); 4 eps stops the tail of sweeps that only chase
     // rounding noise (eigenvalues move by O(a_pq^2 / gap), the eigenvector basis stays a product of exact rotations)
     double rel_tol = 4.0 * 1.1102230246251565e-16;
-    if (const char* env = getenv("LINALG_B200_JACOBI_TOL")) rel_tol = atof(env) * 1.1102230246251565e-16;
+    static const double env_tol = getenv("LINALG_B200_JACOBI_TOL") ? atof(getenv("LINALG_B200_JACOBI_TOL")) : 0.0;  // read once
+    if (env_tol > 0.0) rel_tol = env_tol * 1.1102230246251565e-16;
     DevBuf Aw, rot, nr, lam, Vraw, ptab;
     LQ_TRY(nr.alloc(c, 16));
     LQ_TRY(lam.alloc(c, sizeof(double) * n));
     LQ_TRY(Vraw.alloc(c, sizeof(double) * (size_t)n * n));
-    if (n <= 128 && getenv("LINALG_B200_JACOBI_TWO_SIDED") == nullptr) {
+    if (n <= 128 && !c->env_jacobi_two_sided) {
         // one-sided kernel: columns in shared memory, padded to a multiple of 16
         const int ne = (n + 15) / 16 * 16, half = ne / 2;
         LQ_TRY(Aw.alloc(c, sizeof(double) * (size_t)ne * ne));
@@ -920,56 +921,167 @@ static int tsqr_householder(Ctx* c, const double* A, long long m, int n, double*
 // convention of linalg/qr.py:39-42).  The second pass restores orthogonality to O(eps) as long as
 // cond(A)^2 * eps << 1; the Cholesky kernel reports a cond(A)^2 estimate and the Householder TSQR tree below
 // takes over when it exceeds 1e10 (or a pivot breaks down).  *used = 0 means "fall back".
-static int tsqr_cholqr2(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded, int* used) {
-    *used = 0;
-    LQ_TRY(eigh_configure(c));
-    DevBuf G, R1, R2, Rinv, Q1, stat;
-    const size_t nn = sizeof(double) * (size_t)n * n;
-    LQ_TRY(G.alloc(c, nn));
-    LQ_TRY(R1.alloc(c, nn));
-    LQ_TRY(R2.alloc(c, nn));
-    LQ_TRY(Rinv.alloc(c, nn));
-    LQ_TRY(stat.alloc(c, 4 * sizeof(double)));
-    double hstat[4] = {0, 0, 0, 0};
+__global__ void tsqr_flags_kernel(double* f, double a, double b) {
+    f[0] = a;
+    f[1] = b;
+}
+
+// status words of one tsqr_cholqr2 call, identical on every rank (they derive from all-reduced data)
+struct CholQrStatus {
+    double chol1_bad = 0, cond2 = 0, chol2_bad = 0, cond2_pass2 = 0;
+    double ranks_short = 0;  // number of ranks whose local block has fewer rows than columns
+    bool ok() const { return chol1_bad == 0.0 && cond2 < 1e10 && chol2_bad == 0.0; }
+};
+
+// scratch of the CholeskyQR2 pipeline (allocated once per call, reused by every column panel of tsqr_wide)
+struct CholQrScratch {
+    DevBuf G, R1, R2, Rinv, Q1;
+    int alloc(Ctx* c, long long m, int n) {
+        const size_t nn = sizeof(double) * (size_t)n * n;
+        LQ_TRY(G.alloc(c, nn + 2 * sizeof(double)));
+        LQ_TRY(R1.alloc(c, nn));
+        LQ_TRY(R2.alloc(c, nn));
+        LQ_TRY(Rinv.alloc(c, nn));
+        LQ_TRY(Q1.alloc(c, sizeof(double) * (size_t)m * n));
+        return LQ_OK;
+    }
+};
+
+// Enqueue one CholeskyQR2 of the m x n block A (row stride lda, n <= 128) -> Q (ldq), R (ldr); nothing is read back.
+// stat[0..3] (device) receive chol1_bad, cond^2 estimate, chol2_bad, cond^2 of pass 2.  `short_flag` >= 0 puts that value
+// into the two spare words behind G so that it is summed over the ranks by the first all-reduce (G[n*n]).
+static int cholqr2_enqueue(Ctx* c, const double* A, int lda, long long m, int n, double* Q, int ldq, double* R, int ldr,
+                           bool sharded, CholQrScratch& w, double* stat, double short_flag) {
+    const bool new_chol = n <= 128 && !c->env_old_chol;
+    double* G = w.G.as<double>();
+    const bool carry = short_flag >= 0.0;
+    if (carry) {
+        tsqr_flags_kernel<<<1, 1, 0, c->stream>>>(G + (size_t)n * n, short_flag, 0.0);
+        LQ_CHECK_LAUNCH(c);
+    }
     // pass 1
-    LQ_TRY(gram(c, A, m, n, G.as<double>()));
-    if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
-    if (n <= 128 && !getenv("LINALG_B200_OLD_CHOL")) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
-    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R1.as<double>(), stat.as<double>());
+    LQ_TRY(gemm(c, true, false, n, n, (int)m, 1.0, A, lda, A, lda, 0.0, G, n));
+    if (sharded) LQ_TRY(comm_allreduce_sum(c, G, (long long)n * n + (carry ? 2 : 0)));
+    if (new_chol) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G, n, w.R1.as<double>(), stat);
+    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G, n, w.R1.as<double>(), stat);
     LQ_CHECK_LAUNCH(c);
-    LQ_COUNT_LAUNCH(c);
-    LQ_CUDA(c, cudaMemcpyAsync(hstat, stat.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (hstat[0] != 0.0 || !(hstat[1] < 1e10)) return LQ_OK;  // ill-conditioned: caller falls back (same on every rank)
-    LQ_TRY(Q1.alloc(c, sizeof(double) * (size_t)m * n));
-    LQ_TRY(launch_triu_inverse(c, R1.as<double>(), n, Rinv.as<double>()));
-    LQ_CHECK_LAUNCH(c);
-    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, Rinv.as<double>(), n, 0.0, Q1.as<double>(), n));
+    LQ_TRY(launch_triu_inverse(c, w.R1.as<double>(), n, w.Rinv.as<double>()));
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, lda, w.Rinv.as<double>(), n, 0.0, w.Q1.as<double>(), n));
     // pass 2
-    LQ_TRY(gram(c, Q1.as<double>(), m, n, G.as<double>()));
-    if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
-    if (n <= 128 && !getenv("LINALG_B200_OLD_CHOL")) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
-    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G.as<double>(), n, R2.as<double>(), stat.as<double>() + 2);
+    LQ_TRY(gemm(c, true, false, n, n, (int)m, 1.0, w.Q1.as<double>(), n, w.Q1.as<double>(), n, 0.0, G, n));
+    if (sharded) LQ_TRY(comm_allreduce_sum(c, G, (long long)n * n));
+    if (new_chol) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G, n, w.R2.as<double>(), stat + 2);
+    else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G, n, w.R2.as<double>(), stat + 2);
     LQ_CHECK_LAUNCH(c);
-    LQ_TRY(launch_triu_inverse(c, R2.as<double>(), n, Rinv.as<double>()));
+    LQ_TRY(launch_triu_inverse(c, w.R2.as<double>(), n, w.Rinv.as<double>()));
+    c->launches += 4 + (carry ? 1 : 0);
+    LQ_TRY(gemm(c, false, false, n, n, n, 1.0, w.R2.as<double>(), n, w.R1.as<double>(), n, 0.0, R, ldr));
+    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, w.Q1.as<double>(), n, w.Rinv.as<double>(), n, 0.0, Q, ldq));
+    return LQ_OK;
+}
+
+static int tsqr_cholqr2(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded, CholQrStatus* st) {
+    // Optimistic pipeline: nothing is read back until the last kernel is queued (round 1 synchronised with the host after
+    // the first Cholesky to look at the cond^2 estimate: a bubble in the middle of a 4 ms call).  The status words and the
+    // "short rank" count ride in the first all-reduce / are computed from all-reduced data, so every rank reaches the same
+    // verdict and a fallback is taken by all ranks together (the path decision must be collective).
+    LQ_TRY(eigh_configure(c));
+    CholQrScratch w;
+    DevBuf stat;
+    LQ_TRY(w.alloc(c, m, n));
+    LQ_TRY(stat.alloc(c, 4 * sizeof(double)));
+    LQ_TRY(cholqr2_enqueue(c, A, n, m, n, Q, n, R, n, sharded, w, stat.as<double>(), m < n ? 1.0 : 0.0));
+    // the one read-back of the call, behind everything else on the stream
+    double h[6] = {0, 0, 0, 0, 0, 0};
+    LQ_CUDA(c, cudaMemcpyAsync(h, stat.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaMemcpyAsync(h + 4, w.G.as<double>() + (size_t)n * n, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    st->chol1_bad = h[0];
+    st->cond2 = (h[1] == h[1]) ? h[1] : 1e300;  // NaN -> ill-conditioned
+    st->chol2_bad = h[2];
+    st->cond2_pass2 = h[3];
+    st->ranks_short = h[4];
+    return LQ_OK;
+}
+
+__global__ void add_inplace_kernel(double* __restrict__ dst, int ldd, const double* __restrict__ src, int lds, int rows, int cols) {
+    const long long total = (long long)rows * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / cols), k = (int)(e % cols);
+        dst[(size_t)i * ldd + k] += src[(size_t)i * lds + k];
+    }
+}
+
+// a7 for n > 128 (e.g. the reference's own benchmark shape 5000 x 1000, linalg/benchmark_qr.py:17): block classical
+// Gram-Schmidt with re-orthogonalisation (BCGS2) over 128-column panels, each panel factored by CholeskyQR2 --
+//   W  = A_k - Q_prev S1,  S1 = Q_prev^T A_k        (first projection)
+//   W' = W   - Q_prev S2,  S2 = Q_prev^T W          (second projection: orthogonality to O(eps))
+//   W' = Q_k R_kk (CholeskyQR2, diag > 0)           R[prev, k] = S1 + S2
+// everything is GEMMs on the FP64 tensor pipe; row-sharded calls all-reduce S1, S2 and the panel Gram matrices.  The
+// status words of all panels are read back once at the end; any ill-conditioned panel sends the whole call to the
+// reflector path (single GPU) or fails alike on every rank (sharded).
+static int tsqr_wide(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
+    const bool sh = sharded && c->nranks > 1;
+    constexpr int PB = 128;
+    const int np = (n + PB - 1) / PB;
+    bool ok = !c->env_tsqr_householder && (sh || m >= 2LL * n);
+    if (ok) {
+        LQ_TRY(eigh_configure(c));
+        CholQrScratch w;
+        DevBuf stat, S;
+        LQ_TRY(w.alloc(c, m, PB));
+        LQ_TRY(stat.alloc(c, sizeof(double) * 4 * np));
+        LQ_TRY(S.alloc(c, sizeof(double) * (size_t)n * PB));
+        LQ_CUDA(c, cudaMemsetAsync(R, 0, sizeof(double) * (size_t)n * n, c->stream));
+        LQ_CUDA(c, cudaMemcpyAsync(Q, A, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToDevice, c->stream));
+        for (int k = 0; k < np; ++k) {
+            const int c0 = k * PB, bk = std::min(PB, n - c0);
+            double* Qk = Q + c0;
+            for (int pass = 0; pass < 2 && c0 > 0; ++pass) {
+                LQ_TRY(gemm(c, true, false, c0, bk, (int)m, 1.0, Q, n, Qk, n, 0.0, S.as<double>(), bk));
+                if (sh) LQ_TRY(comm_allreduce_sum(c, S.as<double>(), (long long)c0 * bk));
+                LQ_TRY(gemm(c, false, false, m, bk, c0, -1.0, Q, n, S.as<double>(), bk, 1.0, Qk, n));
+                add_inplace_kernel<<<grid_for(c, (long long)c0 * bk), 256, 0, c->stream>>>(R + c0, n, S.as<double>(), bk, c0, bk);
+                LQ_CHECK_LAUNCH(c);
+                LQ_COUNT_LAUNCH(c);
+            }
+            LQ_TRY(cholqr2_enqueue(c, Qk, n, m, bk, Qk, n, R + (size_t)c0 * n + c0, n, sh, w, stat.as<double>() + 4 * k, -1.0));
+        }
+        std::vector<double> h(4 * (size_t)np);
+        LQ_CUDA(c, cudaMemcpyAsync(h.data(), stat.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < np; ++k)
+            if (!(h[4 * k] == 0.0 && h[4 * k + 1] < 1e10 && h[4 * k + 2] == 0.0)) ok = false;
+        if (ok) return LQ_OK;
+    }
+    LQ_REQUIRE(c, !sh, LQ_ERR_UNSUPPORTED,
+               "tsqr (sharded, n = %d > 128): a column panel is too ill-conditioned for CholeskyQR2 and the reflector tree "
+               "supports n <= 128", n);
+    LQ_REQUIRE(c, m >= n, LQ_ERR_SHAPE, "tsqr needs m >= n (got %lld x %d)", m, n);
+    DevBuf sgn;
+    LQ_TRY(sgn.alloc(c, sizeof(double) * n));
+    LQ_TRY(blocked_householder_qr(c, A, (int)m, n, Q, R));
+    sign_fix_R_kernel<<<1, 256, 0, c->stream>>>(R, n, sgn.as<double>());
+    scale_cols_tall_kernel<<<grid_for(c, m * n), 256, 0, c->stream>>>(Q, m, n, sgn.as<double>());
     LQ_CHECK_LAUNCH(c);
-    c->launches += 3;
-    LQ_TRY(gemm(c, false, false, n, n, n, 1.0, R2.as<double>(), n, R1.as<double>(), n, 0.0, R, n));
-    LQ_TRY(gemm(c, false, false, m, n, n, 1.0, Q1.as<double>(), n, Rinv.as<double>(), n, 0.0, Q, n));
-    *used = 1;
+    c->launches += 2;
     return LQ_OK;
 }
 
 // a7: thin QR of a tall-skinny matrix with diag(R) > 0.
 int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded) {
-    LQ_REQUIRE(c, m >= n && n >= 1, LQ_ERR_SHAPE, "tsqr needs m >= n >= 1 (got %lld x %d)", m, n);
-    LQ_REQUIRE(c, n <= 128, LQ_ERR_UNSUPPORTED, "tsqr supports n <= 128 (got %d); use householder_qr", n);
-    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "tsqr: more than 2^31 rows per device not supported");
     const bool sh = sharded && c->nranks > 1;
-    if (!getenv("LINALG_B200_TSQR_HOUSEHOLDER") && m >= 4LL * n) {
-        int used = 0;
-        LQ_TRY(tsqr_cholqr2(c, A, m, n, Q, R, sh, &used));
-        if (used) return LQ_OK;
+    // Row-sharded calls validate only what every rank sees alike (n); the rank-local row count is checked through the
+    // all-reduced "short rank" count so that no rank leaves while its peers wait in a collective.
+    LQ_REQUIRE(c, n >= 1 && m >= 1 && (sh || m >= n), LQ_ERR_SHAPE, "tsqr needs m >= n >= 1 (got %lld x %d)", m, n);
+    LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "tsqr: more than 2^31 rows per device not supported");
+    if (n > 128) return tsqr_wide(c, A, m, n, Q, R, sharded);
+    CholQrStatus st;
+    bool have_status = false;
+    if (!c->env_tsqr_householder && (sh || m >= 4LL * n)) {
+        LQ_TRY(tsqr_cholqr2(c, A, m, n, Q, R, sh, &st));
+        if (st.ok()) return LQ_OK;
+        have_status = true;
     }
     if (!sh) {
         // robust path for ill-conditioned (or nearly square) input: the blocked compact-WY Householder QR, whose
@@ -984,7 +1096,20 @@ int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R
         return LQ_OK;
     }
     // row-sharded and ill-conditioned: Householder reduction tree + Q = A R^{-1} with one refinement pass
-    // (orthogonality O(eps), residual O(cond(A) eps))
+    // (orthogonality O(eps), residual O(cond(A) eps)); its leaves need at least n rows on every rank
+    if (!have_status) {
+        DevBuf f;
+        LQ_TRY(f.alloc(c, 2 * sizeof(double)));
+        tsqr_flags_kernel<<<1, 1, 0, c->stream>>>(f.as<double>(), m < n ? 1.0 : 0.0, 0.0);
+        LQ_CHECK_LAUNCH(c);
+        LQ_TRY(comm_allreduce_sum(c, f.as<double>(), 2));
+        double h[2] = {0, 0};
+        LQ_CUDA(c, cudaMemcpyAsync(h, f.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+        st.ranks_short = h[0];
+    }
+    LQ_REQUIRE(c, st.ranks_short == 0.0, LQ_ERR_SHAPE,
+               "tsqr (sharded, reflector path): %d rank(s) hold fewer than n = %d rows; re-shard the rows", (int)st.ranks_short, n);
     return tsqr_householder(c, A, m, n, Q, R, sharded);
 }
 

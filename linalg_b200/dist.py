@@ -99,6 +99,18 @@ def sum_over_ranks(value: float) -> float:
     return float(t.item())
 
 
+def allgather_object(obj):
+    """Every rank returns the list of all ranks' (picklable, small) objects, in rank order."""
+    info = rank_info()
+    if info.world == 1:
+        return [obj]
+    import torch.distributed as dist
+
+    out = [None] * info.world
+    dist.all_gather_object(out, obj)
+    return out
+
+
 def init_comm(ctx, info: RankInfo | None = None):
     """Create the NCCL communicator of ``ctx`` (collective over all ranks of the control plane)."""
     info = info or rank_info()
@@ -131,5 +143,5 @@ def my_row_slice(rows: int, info: RankInfo | None = None, align: int = 1):
 
 __all__ = [
     "RankInfo", "rank_info", "init_control_plane", "shutdown_control_plane", "barrier", "broadcast_bytes",
-    "max_over_ranks", "sum_over_ranks", "init_comm", "my_batch_slice", "my_row_slice",
+    "max_over_ranks", "sum_over_ranks", "allgather_object", "init_comm", "my_batch_slice", "my_row_slice",
 ]

@@ -457,6 +457,47 @@ def test_batched32_pipelined_variant_is_bitwise_identical(ctx, batch):
     assert orc.rel_max_err(out[13][0][: len(Qo)], Qo) <= REL and orc.rel_max_err(out[13][1][: len(Ro)], Ro) <= REL
 
 
+@pytest.mark.parametrize("batch", [1, 5, 31, 33, 1000, 4099])
+def test_batched32_round2_kernels_agree(ctx, batch):
+    """The round-2 kernels of a1 at 32 x 32 -- the default (variant 0: lane = column, left-looking panels, Q formed by
+    compact-WY block reflectors on DMMA.8x8x4), the two-stage left-looking kernel (36) and the round-1 R phase with the
+    DMMA Q phase (21) -- against the reference semantics (oracle, 1e-10) and against the round-1 kernel (14), with ragged
+    tails, a skipped reflector (qr.py:79: zero column), a dependent column and a badly scaled matrix."""
+    rng = np.random.default_rng(900 + batch)
+    A = rng.standard_normal((batch, 32, 32))
+    if batch > 16:
+        A[3, :, 5] = 0.0            # skipped reflector
+        A[7, :, 9] = A[7, :, 2]     # dependent column
+        A[11] *= 1e-9               # small scale (absolute 1e-12 threshold not reached)
+        A[12] *= 1e7
+        A[13, :, 0] = 0.0           # first column skipped
+        A[14, :, 31] = 0.0          # last column skipped
+    dA = ctx.upload(A)
+    out = {}
+    for v in (14, 0, 36, 21, 52):
+        dQ, dR = ctx.upload(np.full_like(A, np.nan)), ctx.upload(np.full_like(A, np.nan))
+        ctx.call("lq_householder_qr_batched_dev", dA.ptr, batch, 32, 32, dQ.ptr, dR.ptr, v)
+        out[v] = (ctx.download(dQ, A.shape), ctx.download(dR, A.shape))
+        Qv, Rv = out[v]
+        assert np.isfinite(Qv).all() and np.isfinite(Rv).all(), v
+        assert np.all(np.tril(Rv, -1) == 0.0), v
+    nref = min(batch, 48)
+    Qo, Ro = orc.householder_qr_batched(A[:nref])
+    for v, (Qv, Rv) in out.items():
+        for i in range(nref):
+            if batch > 16 and i == 7:
+                # dependent column: the reflector of column 9 is built from rounding noise, Q is not unique there;
+                # the invariants still hold
+                assert orc.qr_residual(A[i], Qv[i], Rv[i]) <= 1e-12 and orc.orth_error(Qv[i]) <= 1e-12, (v, i)
+                continue
+            assert orc.rel_max_err(Qv[i], Qo[i]) <= REL and orc.rel_max_err(Rv[i], Ro[i]) <= REL, (v, i)
+    # every matrix of the batch: invariants, and agreement with the round-1 kernel
+    for v, (Qv, Rv) in out.items():
+        resid = np.linalg.norm(A - Qv @ Rv, axis=(1, 2)) / np.linalg.norm(A, axis=(1, 2))
+        orth = np.abs(np.swapaxes(Qv, 1, 2) @ Qv - np.eye(32)).max(axis=(1, 2))
+        assert resid.max() <= 1e-12 and orth.max() <= 1e-12, (v, resid.max(), orth.max())
+
+
 @pytest.mark.parametrize("m", [33, 64, 300, 1000, 4096, 8192])
 def test_panel_kernels_agree(ctx, m):
     """The three panel factorisations of the blocked path (barrier.cluster kernel, st.async kernels with 512 / 256
@@ -487,22 +528,19 @@ def test_panel_kernels_agree(ctx, m):
 
 
 def test_eigh_one_sided_matches_two_sided(ctx):
-    """n <= 128 runs the one-sided block round-robin Jacobi; LINALG_B200_JACOBI_TWO_SIDED selects the two-sided kernel."""
-    import os
-
+    """n <= 128 runs the one-sided block round-robin Jacobi; the JACOBI_TWO_SIDED option selects the two-sided kernel."""
     for n, rows in ((128, 4096), (128, 100), (96, 500), (33, 40)):
         M = np.random.default_rng(n + rows).standard_normal((rows, n))
         G = M.T @ M
         res = {}
         for two in (False, True):
-            if two:
-                os.environ["LINALG_B200_JACOBI_TWO_SIDED"] = "1"
+            ctx.set_option("JACOBI_TWO_SIDED", two)
             try:
                 dG, dl, dV = ctx.upload(G), ctx.alloc(8 * n), ctx.alloc(8 * n * n)
                 ctx.call("lq_eigh_dev", dG.ptr, n, dl.ptr, dV.ptr)
                 res[two] = (ctx.download(dl, (n,)), ctx.download(dV, (n, n)))
             finally:
-                os.environ.pop("LINALG_B200_JACOBI_TWO_SIDED", None)
+                ctx.set_option("JACOBI_TWO_SIDED", False)
         ref = np.linalg.eigvalsh(G)[::-1]
         for lam, V in res.values():
             assert np.max(np.abs(lam - ref)) <= 1e-12 * ref[0]
