@@ -45,6 +45,14 @@ PER_GPU_BATCH = 1 << 20
 UNIQUE = 1 << 16                                 # distinct random matrices, tiled to the full batch
 
 
+
+def _json_default(o):
+    """NumPy scalars (np.bool_, np.float64, np.int64) that slipped into the line."""
+    if hasattr(o, "item"):
+        return o.item()
+    raise TypeError(f"not JSON serialisable: {type(o).__name__}")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -203,7 +211,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=_json_default), flush=True)
     return 0
 
 
@@ -448,7 +456,7 @@ def main():
             "device": {"sm_count": props["sm_count"], "cc": f"{props['cc_major']}.{props['cc_minor']}", "mem_mib": props["mem_mib"]},
             "extras": extras,
         }
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        os.write(json_fd, (json.dumps(line, default=_json_default) + "\n").encode())
     d.barrier()
     ctx.close()
     d.shutdown_control_plane()

@@ -218,7 +218,9 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
 int lstsq_hh_batched_stream(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n,
                             int nrhs, double* X) {
     if (batch == 0) return LQ_OK;
-    int rc = lstsq_stream_kernel_launch(c, st, A, B, batch, m, n, nrhs, X);
+    int rc = lstsq_tile_kernel_launch(c, st, A, B, batch, m, n, nrhs, X, nullptr, 0);
+    if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    rc = lstsq_stream_kernel_launch(c, st, A, B, batch, m, n, nrhs, X);
     if (rc != LQ_ERR_UNSUPPORTED) return rc;
     const size_t smem = small_hh_smem_doubles(m, n, nrhs) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
@@ -241,6 +243,12 @@ int lstsq_hh_batched_stream(Ctx* c, cudaStream_t st, const double* A, const doub
 int lstsq_mgs_batched_stream(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n,
                              int nrhs, double* X, int* info) {
     if (batch == 0) return LQ_OK;
+    // Only X and the dependence report are observable (linalg/qr.py:103-119): the solution is the one of the
+    // Householder entry point and |R[j][j]| does not depend on how the QR factorisation was computed.
+    {
+        const int rc = lstsq_tile_kernel_launch(c, st, A, B, batch, m, n, nrhs, X, info, 1);
+        if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    }
     const size_t smem = small_mgs_smem_doubles(m, n, nrhs) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
         static DeviceLatch configured;
@@ -389,7 +397,8 @@ int lq_lstsq_householder_batched(lq_ctx* h, const double* A, const double* B, in
     LQ_REQUIRE(c, m >= n && nrhs >= 1, LQ_ERR_SHAPE, "least squares needs m >= n and nrhs >= 1 (got %d x %d, %d rhs)", m,
                n, nrhs);
     const size_t mn = (size_t)m * n * 8, mk = (size_t)m * nrhs * 8, nk = (size_t)n * nrhs * 8;
-    if (!fits_small(c, small_hh_smem_doubles(m, n, nrhs)) && !lstsq_stream_kernel_supported(m, n, nrhs)) {
+    if (!fits_small(c, small_hh_smem_doubles(m, n, nrhs)) && !lstsq_stream_kernel_supported(m, n, nrhs) &&
+        !lstsq_tile_kernel_supported(m, n, nrhs)) {
         LQ_CUDA(c, cudaSetDevice(c->device));
         for (int64_t b = 0; b < batch; ++b) {
             DevBuf dA, dB, dX;
@@ -426,7 +435,7 @@ int lq_lstsq_mgs_batched(lq_ctx* h, const double* A, const double* B, int64_t ba
     LQ_ARGS_QR(c, A, batch, m, n);
     LQ_REQUIRE(c, nrhs >= 1, LQ_ERR_SHAPE, "nrhs must be >= 1");
     const size_t mn = (size_t)m * n * 8, mk = (size_t)m * nrhs * 8, nk = (size_t)n * nrhs * 8;
-    if (!fits_small(c, small_mgs_smem_doubles(m, n, nrhs))) {
+    if (!fits_small(c, small_mgs_smem_doubles(m, n, nrhs)) && !lstsq_tile_kernel_supported(m, n, nrhs)) {
         LQ_CUDA(c, cudaSetDevice(c->device));
         for (int64_t b = 0; b < batch; ++b) {
             DevBuf dA, dB, dX, dI;

@@ -41,6 +41,12 @@ bool lstsq_stream_kernel_supported(int m, int n, int nrhs);
 int lstsq_stream_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m,
                                int n, int nrhs, double* X);  // LQ_ERR_UNSUPPORTED if the shape is not covered
 
+// round 2: one warp per system, block reflectors on DMMA (n <= 64, nrhs <= 16).  info (may be null): per system, 0 or
+// 1 + the first column with |R[j][j]| < 1e-12 (info_mode 1, the MGS test of linalg/qr.py:40-41) / == 0 (info_mode 2)
+bool lstsq_tile_kernel_supported(int m, int n, int nrhs);
+int lstsq_tile_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n,
+                             int nrhs, double* X, int* info, int info_mode);
+
 // ---- tallskinny.cu
 int gram(Ctx* c, const double* A, long long m, int n, double* G);  // G = A^T A
 int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V);
