@@ -38,12 +38,11 @@ struct LsTile {
     __host__ __device__ static constexpr int tile(int cb, int p) { return 8 * p - (p * (p - 1)) / 2 + (cb - p); }
     static constexpr int A_TILES = 36;
     static constexpr int Y_TILE0 = A_TILES;                 // y tile (rt, p) at Y_TILE0 + 8 * rt + p
-    static constexpr int XC = (A_TILES + 8 * NRT) * 64;     // 2 x 32: the published column (double buffered)
-    static constexpr int XS = XC + 64;                      // 32 rows x stride 10: the panel's reflectors, row-major
-    static constexpr int XS_STRIDE = 10;
-    static constexpr int GS = XS + ROWS * XS_STRIDE;        // 64: Gram matrix, then scratch of the back-substitution
-    static constexpr int TS = GS + 64;                      // 64: -T
-    static constexpr int DV = TS + 64;                      // 8: v0 of the panel's reflectors
+    static constexpr int XS = (A_TILES + 8 * NRT) * 64;     // 32 rows x stride 10: the panel's reflectors, row-major
+    static constexpr int XS_STRIDE = 10;                    // (also the scratch of the back-substitution)
+    static constexpr int TS = XS + ROWS * XS_STRIDE;        // 64: -T
+    static constexpr int GS = TS + 64;                      // 2 x 8: column k of the Gram matrix X^T X (double buffered)
+    static constexpr int DV = GS + 16;                      // 8: v0 of the panel's reflectors
     static constexpr int WARP_DOUBLES = DV + 8;
 };
 static_assert(LsTile::tile(7, 7) == 35, "packed triangle");
@@ -55,7 +54,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     lstsq_tile_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ X, int* __restrict__ info,
                       long long batch, int m, int n, int nrhs, int info_mode) {
     using L = LsTile;
-    constexpr int NCB = L::NCB, NRT = L::NRT, RB = L::RB;
+    constexpr int NCB = L::NCB, NRT = L::NRT, RB = L::RB, XSTR = L::XS_STRIDE;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -63,10 +62,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     if (sys >= batch) return;  // warps never synchronise with each other
 
     double* Rt = sm + (size_t)warp * L::WARP_DOUBLES;
-    double* Xc = Rt + L::XC;
     double* Xs = Rt + L::XS;
-    double* Gs = Rt + L::GS;
     double* Ts = Rt + L::TS;
+    double* Gs = Rt + L::GS;
     double* Dv = Rt + L::DV;
 
     const double* Ag = A + sys * (long long)m * n;
@@ -76,7 +74,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
     {
         const double2 z = make_double2(0.0, 0.0);
-        for (int e = lane; e < L::XC / 2; e += 32) reinterpret_cast<double2*>(Rt)[e] = z;
+        for (int e = lane; e < L::XS / 2; e += 32) reinterpret_cast<double2*>(Rt)[e] = z;
     }
     __syncwarp();
 
@@ -121,34 +119,59 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     for (int rb = 0; rb < RB; ++rb) P[rb][0] = ct[cb][rb][0], P[rb][1] = ct[cb][rb][1];
                 }
             double* rpp = Rt + L::tile(p, p) * 64;  // diagonal tile of R^T: [c][i] = R[8p + i][8p + c]
+            double* xrow = Xs + (2 * t) * XSTR;     // + 8 rb XSTR (+ XSTR): rows 8 rb + 2 t (+ 1) of the published reflectors
 
-            // ---- factor the 8 columns of [R_pp ; P]
-            double bts[8];
+            // ---- factor the 8 columns of [R_pp ; P].  T (dlarft, forward / columnwise) is built on the way, off the
+            // critical chain: column k of the Gram matrix X^T X falls out of step k's dot products (lanes g < k), is
+            // broadcast through shared memory and consumed during step k + 1:
+            //     T[g][k] = -beta_k sum_{m = g}^{k - 1} T[g][m] G[m][k]
+            double Trow[8];
+            double beta_prev = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                double* xc = Xc + (j & 1) * 32;
                 if (g == j) {
 #pragma unroll
-                    for (int rb = 0; rb < RB; ++rb) *reinterpret_cast<double2*>(xc + 8 * rb + 2 * t) = make_double2(P[rb][0], P[rb][1]);
+                    for (int rb = 0; rb < RB; ++rb) {
+                        xrow[8 * rb * XSTR + j] = P[rb][0];
+                        xrow[(8 * rb + 1) * XSTR + j] = P[rb][1];
+                    }
                 }
                 const double rjc = rpp[g * 8 + j];  // R[j][c = g]
                 const double x0 = rpp[j * 8 + j];
                 __syncwarp();
-                double2 xk[RB];
-                double d0 = 0.0, d1 = 0.0;
+                double xk[RB][2];
+                double d0 = 0.0, d1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
-                    xk[rb] = *reinterpret_cast<const double2*>(xc + 8 * rb + 2 * t);
-                    d0 = fma(xk[rb].x, P[rb][0], d0);
-                    d1 = fma(xk[rb].y, P[rb][1], d1);
+                    xk[rb][0] = xrow[8 * rb * XSTR + j];
+                    xk[rb][1] = xrow[(8 * rb + 1) * XSTR + j];
+                    d0 = fma(xk[rb][0], P[rb][0], d0);
+                    d1 = fma(xk[rb][1], P[rb][1], d1);
+                    q0 = fma(xk[rb][0], xk[rb][0], q0);
+                    q1 = fma(xk[rb][1], xk[rb][1], q1);
                 }
-                double d = d0 + d1;
+                double d = d0 + d1, q = q0 + q1;
                 d += __shfl_xor_sync(0xffffffffu, d, 1);
-                d += __shfl_xor_sync(0xffffffffu, d, 2);                 // x^T a_c for c = g
-                const double ssb = __shfl_sync(0xffffffffu, d, 4 * j);  // x^T x
+                q += __shfl_xor_sync(0xffffffffu, q, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);  // x^T a_c for c = g
+                q += __shfl_xor_sync(0xffffffffu, q, 2);  // x^T x
 
-                const double ssc = fmax(fma(x0, x0, ssb), 1e-300);
-                // y = 1 / ||v_full||, beta = 2 / v^T v = y^2 / (1 + |x0| y); the reciprocal is seeded from the UNREFINED y
+                // column j - 1 of T (needs G[.][j - 1], published in the previous step, and beta_{j-1})
+                if (j > 0) {
+                    const double* gk = Gs + ((j - 1) & 1) * 8;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int mm = 0; mm < j - 1; ++mm) {
+                        if (mm & 1) a1 = fma(Trow[mm], gk[mm], a1);
+                        else a0 = fma(Trow[mm], gk[mm], a0);
+                    }
+                    const double sel = (g == j - 1) ? 1.0 : 0.0, lt = (g < j - 1) ? 1.0 : 0.0;
+                    Trow[j - 1] = beta_prev * fma(-lt, a0 + a1, sel);
+                }
+                if (t == 0 && g < j) Gs[(j & 1) * 8 + g] = d;
+
+                const double ssc = fma(x0, x0, q) + 1e-300;
+                // y = 1 / ||[x0 ; x]||, beta = 2 / v^T v = y^2 / (1 + |x0| y); the reciprocal is seeded from the UNREFINED y
                 const double ax0 = fabs(x0);
                 double y = rsqrt_seed(ssc);
                 double u = rcp_seed(fma(ax0, y, 1.0));
@@ -169,56 +192,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 const double alpha = copysign(nrm, x0);
                 const double v0 = skip ? 0.0 : x0 + alpha;
                 const double beta = skip ? 0.0 : (y * y) * u;
-                bts[j] = beta;
+                beta_prev = beta;
 
                 const double s = (g > j) ? beta * fma(v0, rjc, d) : 0.0;
-                if (t == 0) {
-                    if (g > j) rpp[g * 8 + j] = fma(-s, v0, rjc);
-                    else if (g == j && !skip) rpp[g * 8 + j] = -alpha;
+                {
+                    const double val = (g > j) ? fma(-s, v0, rjc) : -alpha;
+                    if (t == 0 && (g > j || (g == j && !skip))) rpp[g * 8 + j] = val;
                 }
                 if (lane == 0) Dv[j] = v0;
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
-                    P[rb][0] = fma(-s, xk[rb].x, P[rb][0]);
-                    P[rb][1] = fma(-s, xk[rb].y, P[rb][1]);
+                    P[rb][0] = fma(-s, xk[rb][0], P[rb][0]);
+                    P[rb][1] = fma(-s, xk[rb][1], P[rb][1]);
                 }
             }
-
-            // ---- reflectors row-major for the update's B operands; Gram matrix X^T X
-            {
-                double G[2] = {0.0, 0.0};
-#pragma unroll
-                for (int rb = 0; rb < RB; ++rb)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        Xs[(8 * rb + 2 * t + e) * L::XS_STRIDE + g] = P[rb][e];
-                        dmma_8x8x4(G, P[rb][e], P[rb][e]);
-                    }
-                *reinterpret_cast<double2*>(Gs + g * 8 + 2 * t) = make_double2(G[0], G[1]);
-            }
+            // last column of T, then -T row g to shared memory (B operands need it transposed)
             __syncwarp();
-            // ---- -T, row g (dlarft, forward / columnwise): T[g][k] = -beta_k sum_{m=g}^{k-1} T[g][m] G[m][k]
             {
-                double acc[8], Tn[8];
+                const double* gk = Gs + 8;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const double sel = (k == g) ? 1.0 : 0.0, gt = (k > g) ? 1.0 : 0.0;
-                    const double tk = bts[k] * fma(-gt, acc[k], sel);
-                    Tn[k] = -tk;
-                    if (k < 7) {
-#pragma unroll
-                        for (int kk = (k + 1) & ~1; kk < 8; kk += 2) {
-                            const double2 g2 = *reinterpret_cast<const double2*>(Gs + k * 8 + kk);
-                            if (kk > k) acc[kk] = fma(tk, g2.x, acc[kk]);
-                            acc[kk + 1] = fma(tk, g2.y, acc[kk + 1]);
-                        }
-                    }
+                for (int mm = 0; mm < 7; ++mm) {
+                    if (mm & 1) a1 = fma(Trow[mm], gk[mm], a1);
+                    else a0 = fma(Trow[mm], gk[mm], a0);
                 }
+                const double sel = (g == 7) ? 1.0 : 0.0, lt = (g < 7) ? 1.0 : 0.0;
+                Trow[7] = beta_prev * fma(-lt, a0 + a1, sel);
                 if (t == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Ts + g * 8 + k) = make_double2(Tn[k], Tn[k + 1]);
+                    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Ts + g * 8 + k) = make_double2(-Trow[k], -Trow[k + 1]);
                 }
             }
             __syncwarp();
@@ -226,37 +228,64 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             const double2 d2 = *reinterpret_cast<const double2*>(Dv + 2 * t);
             double2 Xt[RB];
 #pragma unroll
-            for (int rb = 0; rb < RB; ++rb) Xt[rb] = *reinterpret_cast<const double2*>(Xs + (8 * rb + g) * L::XS_STRIDE + 2 * t);
+            for (int rb = 0; rb < RB; ++rb) Xt[rb] = *reinterpret_cast<const double2*>(Xs + (8 * rb + g) * XSTR + 2 * t);
 
-            // ---- block reflector on the trailing column blocks and the right-hand sides
-            auto apply = [&](double* rtile, double (&c)[RB][2]) {
-                double2 r = *reinterpret_cast<const double2*>(rtile + g * 8 + 2 * t);
-                double wa[2] = {r.x * d2.x, r.y * d2.y}, wb[2] = {0.0, 0.0};
+            // ---- block reflector on the trailing column blocks and the right-hand sides, three tiles at a time (the
+            // accumulator chains of the tiles interleave).  A tile left of the panel inside an active group is dead for
+            // the rest of this block: it is processed too (no branch) and only its store to R is suppressed.
+            auto apply3 = [&](double* ta, bool oa, double (&ca)[RB][2], double* tb, bool ob, double (&cbk)[RB][2], double* tc, bool oc,
+                              double (&cc)[RB][2]) {
+                double2 ra = *reinterpret_cast<const double2*>(ta + g * 8 + 2 * t);
+                double2 rb2 = *reinterpret_cast<const double2*>(tb + g * 8 + 2 * t);
+                double2 rc = *reinterpret_cast<const double2*>(tc + g * 8 + 2 * t);
+                double wa[2] = {ra.x * d2.x, ra.y * d2.y}, wa2[2] = {0.0, 0.0};
+                double wb[2] = {rb2.x * d2.x, rb2.y * d2.y}, wb2[2] = {0.0, 0.0};
+                double wc[2] = {rc.x * d2.x, rc.y * d2.y}, wc2[2] = {0.0, 0.0};
 #pragma unroll
-                for (int rb = 0; rb < RB; rb += 2) {
-                    dmma_8x8x4(wa, c[rb][0], P[rb][0]);
-                    dmma_8x8x4(wb, c[rb + 1][0], P[rb + 1][0]);
-                    dmma_8x8x4(wa, c[rb][1], P[rb][1]);
-                    dmma_8x8x4(wb, c[rb + 1][1], P[rb + 1][1]);
+                for (int rb = 0; rb < RB; rb += 2)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        dmma_8x8x4(wa, ca[rb][e], P[rb][e]);
+                        dmma_8x8x4(wb, cbk[rb][e], P[rb][e]);
+                        dmma_8x8x4(wc, cc[rb][e], P[rb][e]);
+                        dmma_8x8x4(wa2, ca[rb + 1][e], P[rb + 1][e]);
+                        dmma_8x8x4(wb2, cbk[rb + 1][e], P[rb + 1][e]);
+                        dmma_8x8x4(wc2, cc[rb + 1][e], P[rb + 1][e]);
+                    }
+                wa[0] += wa2[0], wa[1] += wa2[1];
+                wb[0] += wb2[0], wb[1] += wb2[1];
+                wc[0] += wc2[0], wc[1] += wc2[1];
+                double za[2] = {0.0, 0.0}, zb[2] = {0.0, 0.0}, zc[2] = {0.0, 0.0};
+                dmma_8x8x4(za, wa[0], nT0);
+                dmma_8x8x4(zb, wb[0], nT0);
+                dmma_8x8x4(zc, wc[0], nT0);
+                dmma_8x8x4(za, wa[1], nT1);
+                dmma_8x8x4(zb, wb[1], nT1);
+                dmma_8x8x4(zc, wc[1], nT1);
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) {
+                    dmma_8x8x4(ca[rb], za[0], Xt[rb].x);
+                    dmma_8x8x4(cbk[rb], zb[0], Xt[rb].x);
+                    dmma_8x8x4(cc[rb], zc[0], Xt[rb].x);
                 }
-                wa[0] += wb[0];
-                wa[1] += wb[1];
-                double w2[2] = {0.0, 0.0};
-                dmma_8x8x4(w2, wa[0], nT0);
-                dmma_8x8x4(w2, wa[1], nT1);
 #pragma unroll
-                for (int rb = 0; rb < RB; ++rb) dmma_8x8x4(c[rb], w2[0], Xt[rb].x);
-#pragma unroll
-                for (int rb = 0; rb < RB; ++rb) dmma_8x8x4(c[rb], w2[1], Xt[rb].y);
-                r.x = fma(w2[0], d2.x, r.x);
-                r.y = fma(w2[1], d2.y, r.y);
-                *reinterpret_cast<double2*>(rtile + g * 8 + 2 * t) = r;
+                for (int rb = 0; rb < RB; ++rb) {
+                    dmma_8x8x4(ca[rb], za[1], Xt[rb].y);
+                    dmma_8x8x4(cbk[rb], zb[1], Xt[rb].y);
+                    dmma_8x8x4(cc[rb], zc[1], Xt[rb].y);
+                }
+                ra.x = fma(za[0], d2.x, ra.x), ra.y = fma(za[1], d2.y, ra.y);
+                rb2.x = fma(zb[0], d2.x, rb2.x), rb2.y = fma(zb[1], d2.y, rb2.y);
+                rc.x = fma(zc[0], d2.x, rc.x), rc.y = fma(zc[1], d2.y, rc.y);
+                if (oa) *reinterpret_cast<double2*>(ta + g * 8 + 2 * t) = ra;
+                if (ob) *reinterpret_cast<double2*>(tb + g * 8 + 2 * t) = rb2;
+                if (oc) *reinterpret_cast<double2*>(tc + g * 8 + 2 * t) = rc;
             };
-#pragma unroll
-            for (int cb = 1; cb < NCB; ++cb)
-                if (cb > p) apply(Rt + L::tile(cb, p) * 64, ct[cb]);
-#pragma unroll
-            for (int rt = 0; rt < NRT; ++rt) apply(Rt + (L::Y_TILE0 + 8 * rt + p) * 64, ct[NCB + rt]);
+            // address of tile (cb, p); an inactive tile (cb <= p) reads its own diagonal tile instead (any valid address)
+            auto taddr = [&](int cb) -> double* { return Rt + L::tile(cb, cb > p ? p : cb) * 64; };
+            apply3(Rt + (L::Y_TILE0 + p) * 64, true, ct[NCB], Rt + (L::Y_TILE0 + 8 + p) * 64, true, ct[NCB + 1], taddr(7), 7 > p, ct[7]);
+            if (p < 6) apply3(taddr(6), true, ct[6], taddr(5), 5 > p, ct[5], taddr(4), 4 > p, ct[4]);
+            if (p < 3) apply3(taddr(3), true, ct[3], taddr(2), 2 > p, ct[2], taddr(1), 1 > p, ct[1]);
             __syncwarp();
         }
     }
@@ -305,14 +334,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             __syncwarp();
 #pragma unroll
             for (int rt = 0; rt < NRT; ++rt)
-                *reinterpret_cast<double2*>(Gs + rt * 64 + g * 8 + 2 * t) = make_double2(xt[rt][ib][0], xt[rt][ib][1]);
+                *reinterpret_cast<double2*>(Xs + rt * 64 + g * 8 + 2 * t) = make_double2(xt[rt][ib][0], xt[rt][ib][1]);
             const double* dt = Rt + L::tile(ib, ib) * 64;  // R[i][j] = dt[j * 8 + i]
             const double rd = dt[(lane & 7) * 9];
             const double rinv_l = (8 * ib + (lane & 7) < n) ? 1.0 / rd : 0.0;
             __syncwarp();
             double z[8];
             {
-                const double* zs = Gs + (lane & 15) * 8;
+                const double* zs = Xs + (lane & 15) * 8;
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
                     const double2 z2 = *reinterpret_cast<const double2*>(zs + i);
@@ -329,14 +358,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             }
             __syncwarp();
             if (lane < 16) {
-                double* zs = Gs + lane * 8;
+                double* zs = Xs + lane * 8;
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(zs + i) = make_double2(z[i], z[i + 1]);
             }
             __syncwarp();
 #pragma unroll
             for (int rt = 0; rt < NRT; ++rt) {
-                const double2 x2 = *reinterpret_cast<const double2*>(Gs + rt * 64 + g * 8 + 2 * t);
+                const double2 x2 = *reinterpret_cast<const double2*>(Xs + rt * 64 + g * 8 + 2 * t);
                 xt[rt][ib][0] = x2.x;
                 xt[rt][ib][1] = x2.y;
             }
