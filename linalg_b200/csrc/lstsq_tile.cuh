@@ -25,6 +25,8 @@
 // 30.1 KB per warp, 7 warps per SM.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lq {
@@ -230,14 +232,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) Xt[rb] = *reinterpret_cast<const double2*>(Xs + (8 * rb + g) * XSTR + 2 * t);
 
-            // ---- block reflector on the trailing column blocks and the right-hand sides, three tiles at a time (the
-            // accumulator chains of the tiles interleave).  A tile left of the panel inside an active group is dead for
-            // the rest of this block: it is processed too (no branch) and only its store to R is suppressed.
-            auto apply3 = [&](double* ta, bool oa, double (&ca)[RB][2], double* tb, bool ob, double (&cbk)[RB][2], double* tc, bool oc,
-                              double (&cc)[RB][2]) {
-                double2 ra = *reinterpret_cast<const double2*>(ta + g * 8 + 2 * t);
-                double2 rb2 = *reinterpret_cast<const double2*>(tb + g * 8 + 2 * t);
-                double2 rc = *reinterpret_cast<const double2*>(tc + g * 8 + 2 * t);
+            // ---- block reflector on the trailing column blocks and the right-hand sides, up to three tiles at a time (the
+            // accumulator chains of the tiles of a group interleave; NT is a compile-time count, so a group never
+            // computes a tile left of the panel)
+            auto apply = [&](auto nt_tag, double* ta, double (&ca)[RB][2], double* tb, double (&cbk)[RB][2], double* tc, double (&cc)[RB][2]) {
+                constexpr int NT = decltype(nt_tag)::value;
+                double2 ra = *reinterpret_cast<const double2*>(ta + g * 8 + 2 * t), rb2 = ra, rc = ra;
+                if (NT > 1) rb2 = *reinterpret_cast<const double2*>(tb + g * 8 + 2 * t);
+                if (NT > 2) rc = *reinterpret_cast<const double2*>(tc + g * 8 + 2 * t);
                 double wa[2] = {ra.x * d2.x, ra.y * d2.y}, wa2[2] = {0.0, 0.0};
                 double wb[2] = {rb2.x * d2.x, rb2.y * d2.y}, wb2[2] = {0.0, 0.0};
                 double wc[2] = {rc.x * d2.x, rc.y * d2.y}, wc2[2] = {0.0, 0.0};
@@ -246,46 +248,60 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         dmma_8x8x4(wa, ca[rb][e], P[rb][e]);
-                        dmma_8x8x4(wb, cbk[rb][e], P[rb][e]);
-                        dmma_8x8x4(wc, cc[rb][e], P[rb][e]);
+                        if (NT > 1) dmma_8x8x4(wb, cbk[rb][e], P[rb][e]);
+                        if (NT > 2) dmma_8x8x4(wc, cc[rb][e], P[rb][e]);
                         dmma_8x8x4(wa2, ca[rb + 1][e], P[rb + 1][e]);
-                        dmma_8x8x4(wb2, cbk[rb + 1][e], P[rb + 1][e]);
-                        dmma_8x8x4(wc2, cc[rb + 1][e], P[rb + 1][e]);
+                        if (NT > 1) dmma_8x8x4(wb2, cbk[rb + 1][e], P[rb + 1][e]);
+                        if (NT > 2) dmma_8x8x4(wc2, cc[rb + 1][e], P[rb + 1][e]);
                     }
                 wa[0] += wa2[0], wa[1] += wa2[1];
                 wb[0] += wb2[0], wb[1] += wb2[1];
                 wc[0] += wc2[0], wc[1] += wc2[1];
                 double za[2] = {0.0, 0.0}, zb[2] = {0.0, 0.0}, zc[2] = {0.0, 0.0};
                 dmma_8x8x4(za, wa[0], nT0);
-                dmma_8x8x4(zb, wb[0], nT0);
-                dmma_8x8x4(zc, wc[0], nT0);
+                if (NT > 1) dmma_8x8x4(zb, wb[0], nT0);
+                if (NT > 2) dmma_8x8x4(zc, wc[0], nT0);
                 dmma_8x8x4(za, wa[1], nT1);
-                dmma_8x8x4(zb, wb[1], nT1);
-                dmma_8x8x4(zc, wc[1], nT1);
+                if (NT > 1) dmma_8x8x4(zb, wb[1], nT1);
+                if (NT > 2) dmma_8x8x4(zc, wc[1], nT1);
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
                     dmma_8x8x4(ca[rb], za[0], Xt[rb].x);
-                    dmma_8x8x4(cbk[rb], zb[0], Xt[rb].x);
-                    dmma_8x8x4(cc[rb], zc[0], Xt[rb].x);
+                    if (NT > 1) dmma_8x8x4(cbk[rb], zb[0], Xt[rb].x);
+                    if (NT > 2) dmma_8x8x4(cc[rb], zc[0], Xt[rb].x);
                 }
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
                     dmma_8x8x4(ca[rb], za[1], Xt[rb].y);
-                    dmma_8x8x4(cbk[rb], zb[1], Xt[rb].y);
-                    dmma_8x8x4(cc[rb], zc[1], Xt[rb].y);
+                    if (NT > 1) dmma_8x8x4(cbk[rb], zb[1], Xt[rb].y);
+                    if (NT > 2) dmma_8x8x4(cc[rb], zc[1], Xt[rb].y);
                 }
                 ra.x = fma(za[0], d2.x, ra.x), ra.y = fma(za[1], d2.y, ra.y);
-                rb2.x = fma(zb[0], d2.x, rb2.x), rb2.y = fma(zb[1], d2.y, rb2.y);
-                rc.x = fma(zc[0], d2.x, rc.x), rc.y = fma(zc[1], d2.y, rc.y);
-                if (oa) *reinterpret_cast<double2*>(ta + g * 8 + 2 * t) = ra;
-                if (ob) *reinterpret_cast<double2*>(tb + g * 8 + 2 * t) = rb2;
-                if (oc) *reinterpret_cast<double2*>(tc + g * 8 + 2 * t) = rc;
+                *reinterpret_cast<double2*>(ta + g * 8 + 2 * t) = ra;
+                if (NT > 1) {
+                    rb2.x = fma(zb[0], d2.x, rb2.x), rb2.y = fma(zb[1], d2.y, rb2.y);
+                    *reinterpret_cast<double2*>(tb + g * 8 + 2 * t) = rb2;
+                }
+                if (NT > 2) {
+                    rc.x = fma(zc[0], d2.x, rc.x), rc.y = fma(zc[1], d2.y, rc.y);
+                    *reinterpret_cast<double2*>(tc + g * 8 + 2 * t) = rc;
+                }
             };
-            // address of tile (cb, p); an inactive tile (cb <= p) reads its own diagonal tile instead (any valid address)
-            auto taddr = [&](int cb) -> double* { return Rt + L::tile(cb, cb > p ? p : cb) * 64; };
-            apply3(Rt + (L::Y_TILE0 + p) * 64, true, ct[NCB], Rt + (L::Y_TILE0 + 8 + p) * 64, true, ct[NCB + 1], taddr(7), 7 > p, ct[7]);
-            if (p < 6) apply3(taddr(6), true, ct[6], taddr(5), 5 > p, ct[5], taddr(4), 4 > p, ct[4]);
-            if (p < 3) apply3(taddr(3), true, ct[3], taddr(2), 2 > p, ct[2], taddr(1), 1 > p, ct[1]);
+            using N1 = std::integral_constant<int, 1>;
+            using N2 = std::integral_constant<int, 2>;
+            using N3 = std::integral_constant<int, 3>;
+            auto taddr = [&](int cb) -> double* { return Rt + L::tile(cb, p) * 64; };
+            double* y0 = Rt + (L::Y_TILE0 + p) * 64;
+            double* y1 = Rt + (L::Y_TILE0 + 8 + p) * 64;
+            // groups: {rhs 0, rhs 1, 7}, {6, 5, 4}, {3, 2, 1}; the column blocks of a group that lie right of the panel
+            if (p < 7) apply(N3{}, y0, ct[NCB], y1, ct[NCB + 1], taddr(7), ct[7]);
+            else apply(N2{}, y0, ct[NCB], y1, ct[NCB + 1], y1, ct[NCB + 1]);
+            if (p < 4) apply(N3{}, taddr(6), ct[6], taddr(5), ct[5], taddr(4), ct[4]);
+            else if (p == 4) apply(N2{}, taddr(6), ct[6], taddr(5), ct[5], taddr(5), ct[5]);
+            else if (p == 5) apply(N1{}, taddr(6), ct[6], taddr(6), ct[6], taddr(6), ct[6]);
+            if (p < 1) apply(N3{}, taddr(3), ct[3], taddr(2), ct[2], taddr(1), ct[1]);
+            else if (p == 1) apply(N2{}, taddr(3), ct[3], taddr(2), ct[2], taddr(2), ct[2]);
+            else if (p == 2) apply(N1{}, taddr(3), ct[3], taddr(3), ct[3], taddr(3), ct[3]);
             __syncwarp();
         }
     }
