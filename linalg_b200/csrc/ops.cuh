@@ -47,6 +47,9 @@ bool lstsq_tile_kernel_supported(int m, int n, int nrhs);
 int lstsq_tile_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n,
                              int nrhs, double* X, int* info, int info_mode);
 
+// ---- syrk.cu: G (n x n, both triangles) = A^T A for n <= 128, upper-triangle blocks only; LQ_ERR_UNSUPPORTED otherwise
+int syrk_tn(Ctx* c, const double* A, int lda, long long m, int n, double* G, int ldg);
+
 // ---- tallskinny.cu
 int gram(Ctx* c, const double* A, long long m, int n, double* G);  // G = A^T A
 int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V);

@@ -787,9 +787,15 @@ int tsqr_rfactor(Ctx* c, const double* A, int lda, long long m, int n, double* R
 }  // namespace
 
 // ------------------------------------------------------------------ public (internal) ops
-int gram(Ctx* c, const double* A, long long m, int n, double* G) {
-    return gemm(c, true, false, n, n, (int)m, 1.0, A, n, A, n, 0.0, G, n);
+// G = A^T A (A m x n with row stride lda): symmetric rank-k kernel (upper-triangle blocks only, syrk.cu) when the shape
+// allows, the general TN GEMM otherwise
+static int gram_ld(Ctx* c, const double* A, int lda, long long m, int n, double* G) {
+    const int rc = syrk_tn(c, A, lda, m, n, G, n);
+    if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    return gemm(c, true, false, n, n, (int)m, 1.0, A, lda, A, lda, 0.0, G, n);
 }
+
+int gram(Ctx* c, const double* A, long long m, int n, double* G) { return gram_ld(c, A, n, m, n, G); }
 
 int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) {
     LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_UNSUPPORTED, "eigen-solver supports n <= 2048 (got %d)", n);
@@ -960,7 +966,7 @@ static int cholqr2_enqueue(Ctx* c, const double* A, int lda, long long m, int n,
         LQ_CHECK_LAUNCH(c);
     }
     // pass 1
-    LQ_TRY(gemm(c, true, false, n, n, (int)m, 1.0, A, lda, A, lda, 0.0, G, n));
+    LQ_TRY(gram_ld(c, A, lda, m, n, G));
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G, (long long)n * n + (carry ? 2 : 0)));
     if (new_chol) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G, n, w.R1.as<double>(), stat);
     else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G, n, w.R1.as<double>(), stat);
@@ -968,7 +974,7 @@ static int cholqr2_enqueue(Ctx* c, const double* A, int lda, long long m, int n,
     LQ_TRY(launch_triu_inverse(c, w.R1.as<double>(), n, w.Rinv.as<double>()));
     LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, lda, w.Rinv.as<double>(), n, 0.0, w.Q1.as<double>(), n));
     // pass 2
-    LQ_TRY(gemm(c, true, false, n, n, (int)m, 1.0, w.Q1.as<double>(), n, w.Q1.as<double>(), n, 0.0, G, n));
+    LQ_TRY(gram_ld(c, w.Q1.as<double>(), n, m, n, G));
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G, (long long)n * n));
     if (new_chol) chol_upper128_kernel<<<1, 1024, 0, c->stream>>>(G, n, w.R2.as<double>(), stat + 2);
     else chol_upper_kernel<<<1, 1024, CHOL_SMEM, c->stream>>>(G, n, w.R2.as<double>(), stat + 2);
