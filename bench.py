@@ -443,8 +443,8 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": profile_traffic("hh_qr32_kernel"),
-                "peak_source": peaks["source"], "kernel": "hh_qr32_kernel", "kernel_ms": kernel_ms,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": profile_traffic("hh_qr32_c8_kernel"),
+                "peak_source": peaks["source"], "kernel": "hh_qr32_c8_kernel<8,1,3,true>", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": batch * BYTES_PER_MATRIX,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "fp64_frac": (batch * FLOPS_HH32 / (kernel_ms * 1e-3) / 1e12 / fp64["dfma_tflops"]) if fp64.get("dfma_tflops") else None,

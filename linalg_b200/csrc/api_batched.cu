@@ -153,6 +153,9 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 57: return launch_hh32_c8<2, 5, 1, true>(c, st, A, batch, Q, R);
             case 58: return launch_hh32_c8<4, 2, 3, true>(c, st, A, batch, Q, R);
             case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
+            case 64: return launch_hh32_c8<9, 1, 3, true>(c, st, A, batch, Q, R);
+            case 65: return launch_hh32_c8<9, 1, 3, false>(c, st, A, batch, Q, R);
+            case 66: return launch_hh32_c8<7, 1, 3, true>(c, st, A, batch, Q, R);
             case 61: return launch_hh32_c8<4, 2, 1, true>(c, st, A, batch, Q, R);
             case 62: return launch_hh32_c8<4, 2, 1, false>(c, st, A, batch, Q, R);
             case 63: return launch_hh32_c8<4, 2, 2, false>(c, st, A, batch, Q, R);

@@ -243,6 +243,31 @@ def test_blocked_8192_full_size_properties(ctx):
     assert np.allclose(np.abs(np.diag(R))[:8], np.abs(np.diag(np.linalg.qr(A[:, :8])[1])), rtol=1e-10)
 
 
+@pytest.mark.parametrize("n", [6400, 8192])
+def test_blocked_two_range_path_full_R_against_lapack(ctx, n):
+    """Matrices with >= 6144 columns take the two-range trailing update / Q formation (two side streams, split at
+    0.65 n).  Full R and every diagonal sign against LAPACK (np.linalg.qr, R only: ~10 s of host time at 8192^2) with
+    the documented convention difference of linalg/qr.py:82-86 (the reference also reflects the last 1-element column:
+    last row of R negated), elementwise at the north-star tolerance, plus the Q invariants on probes."""
+    A = np.random.default_rng(5 + n).standard_normal((n, n))
+    dA, dQ, dR = ctx.upload(A), ctx.alloc(A.nbytes), ctx.alloc(A.nbytes)
+    ctx.call("lq_householder_qr_dev", dA.ptr, n, n, dQ.ptr, dR.ptr)
+    R = ctx.download(dR, (n, n))
+    Rl = np.linalg.qr(A, mode="r")
+    Rl[-1] *= -1.0
+    assert np.array_equal(np.sign(np.diag(R)), np.sign(np.diag(Rl)))          # every reflector's sign
+    assert orc.rel_max_err(R, Rl) <= REL
+    assert np.max(np.abs(np.diag(R) - np.diag(Rl)) / np.abs(np.diag(Rl))) <= REL
+    assert np.all(np.tril(R, -1) == 0.0)
+    Q = ctx.download(dQ, (n, n))
+    X = np.random.default_rng(6).standard_normal((n, 4))
+    AX = A @ X
+    assert np.linalg.norm(AX - Q @ (R @ X)) / np.linalg.norm(AX) <= 1e-12
+    assert np.linalg.norm(Q.T @ (Q @ X) - X) / np.linalg.norm(X) <= 1e-12
+    for b in (dA, dQ, dR):
+        b.free()
+
+
 def test_gemm_building_block(ctx):
     rng = np.random.default_rng(3)
     for ta, tb, M, N, K in [(0, 0, 200, 136, 48), (1, 0, 128, 256, 4096), (0, 0, 4096, 128, 128), (1, 1, 33, 17, 9),
