@@ -103,6 +103,12 @@ int lq_svd_gram(lq_ctx* ctx, const double* A, int64_t m, int n, double tol, doub
 /* svd.py:67-76: complete U (HOST, m x n, first `rank` columns valid) with an orthonormal basis of the
  * complement built from the caller-drawn candidates Z (HOST, m x (n - rank)); all arithmetic on device. */
 int lq_svd_complete(lq_ctx* ctx, double* U, int64_t m, int n, int rank, const double* Z);
+/* the same with the candidates generated ON THE DEVICE from `seed` (Philox4x32-10 + Box-Muller; deterministic, no m x (n-rank)
+ * upload).  The reference draws them from the global np.random (svd.py:69), i.e. it is not reproducible there; only the
+ * invariants of the completion are pinned by its tests (tests/test_svd.py:60-79). */
+int lq_svd_complete_seeded(lq_ctx* ctx, double* U, int64_t m, int n, int rank, uint64_t seed);
+/* `count` standard-normal doubles of that generator into device memory (a function of (seed, index) only) */
+int lq_random_normal_dev(lq_ctx* ctx, double* out, int64_t count, uint64_t seed);
 /* building blocks (device pointers) */
 int lq_gram_dev(lq_ctx* ctx, const double* A, int64_t m, int n, double* G);          /* G = A^T A (n x n) */
 /* Eigen-decomposition of a symmetric POSITIVE SEMI-DEFINITE matrix (the Gram / covariance matrices of svd.py:42,46 and

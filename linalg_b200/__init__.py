@@ -22,7 +22,7 @@ from .qr import (
     tsqr,
 )
 from .svd import svd
-from .extras import pca, project_onto_colspace
+from .extras import adj, adj_batched, det, det_batched, pca, project_onto_colspace, random_nonsingular_qr_batched
 from .utils import EPS, shard_bounds
 
 __all__ = [
@@ -44,6 +44,11 @@ __all__ = [
     "shard_bounds",
     "project_onto_colspace",
     "pca",
+    "adj",
+    "adj_batched",
+    "det",
+    "det_batched",
+    "random_nonsingular_qr_batched",
 ]
 
 __version__ = "0.1.0"

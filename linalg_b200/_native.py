@@ -58,6 +58,8 @@ SIGNATURES = {
     "lq_svd_gram_dev": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_double, _DP, _DP, _DP, C.POINTER(C.c_int)]),
     "lq_svd_gram": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_double, _DP, _DP, _DP, C.POINTER(C.c_int)]),
     "lq_svd_complete": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_int, _DP]),
+    "lq_svd_complete_seeded": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_int, C.c_uint64]),
+    "lq_random_normal_dev": (C.c_int, [_CTX, _DP, C.c_int64, C.c_uint64]),
     "lq_gram_dev": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, _DP]),
     "lq_eigh_dev": (C.c_int, [_CTX, _DP, C.c_int, _DP, _DP]),
     "lq_gemm_dev": (C.c_int, [_CTX, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, _DP, C.c_int, _DP,
@@ -238,6 +240,63 @@ def default_context() -> Context:
             dev = int(os.environ.get("LINALG_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
             _default_ctx = Context(dev)
         return _default_ctx
+
+
+_device_ctxs: dict = {}
+
+
+def device_context(device: int) -> Context:
+    """Process-wide context of one device (created on first use); the default context is reused for its device."""
+    device = int(device)
+    with _default_lock:
+        if _default_ctx is not None and _default_ctx.device == device:
+            return _default_ctx
+        ctx = _device_ctxs.get(device)
+        if ctx is None:
+            ctx = _device_ctxs[device] = Context(device)
+        return ctx
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    lib = load_library()
+    check(lib, None, lib.lq_device_count(C.byref(n)), "lq_device_count")
+    return int(n.value)
+
+
+def fan_out(devices, total: int, fn, _contexts=None):
+    """Run ``fn(ctx, lo, hi)`` for a contiguous split of ``range(total)`` over ``devices`` -- one host thread and one
+    context per device, no communication (batched problems shard by batch index).  ctypes drops
+    the GIL inside the C call, so the per-device host-pointer pipelines (H2D, kernels, D2H) run concurrently.  The
+    first exception of any device is re-raised after every thread has finished."""
+    from .utils import shard_bounds
+
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise ValueError("devices must name at least one GPU")
+    if len(set(devices)) != len(devices):
+        raise ValueError(f"devices must be distinct, got {devices}")
+    ctxs = [device_context(d) for d in devices] if _contexts is None else list(_contexts)
+    parts = [shard_bounds(total, len(devices), r) for r in range(len(devices))]
+    errors = [None] * len(devices)
+
+    def work(r):
+        lo, hi = parts[r]
+        if hi > lo:
+            try:
+                fn(ctxs[r], lo, hi)
+            except BaseException as exc:  # noqa: BLE001 -- re-raised in the caller's thread
+                errors[r] = exc
+
+    threads = [threading.Thread(target=work, args=(r,), name=f"linalg_b200-dev{devices[r]}") for r in range(1, len(devices))]
+    for t in threads:
+        t.start()
+    work(0)
+    for t in threads:
+        t.join()
+    for exc in errors:
+        if exc is not None:
+            raise exc
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

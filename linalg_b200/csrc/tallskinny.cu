@@ -1119,6 +1119,48 @@ int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R
     return tsqr_householder(c, A, m, n, Q, R, sharded);
 }
 
+
+// ------------------------------------------------------------------ counter-based standard-normal generator
+// Philox4x32-10 (Salmon et al., SC'11: counter = element group, key = seed) + Box-Muller; four doubles per counter.
+// The stream depends only on (seed, element index): any grid shape and any device produce the same numbers.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n2 = hi0 ^ ctr[3] ^ k1;
+        ctr[0] = n0;
+        ctr[1] = lo1;
+        ctr[2] = n2;
+        ctr[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__global__ void __launch_bounds__(256) philox_normal_kernel(double* __restrict__ out, long long count, unsigned long long seed) {
+    const long long groups = (count + 3) / 4;
+    for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+        double z[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t ctr[4] = {(uint32_t)gidx, (uint32_t)((unsigned long long)gidx >> 32), (uint32_t)half, 0x6c696e61u};
+            philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+            // two uniforms in (0, 1] / [0, 1) with 53 / 32 bits, one Box-Muller pair
+            const unsigned long long b = ((unsigned long long)ctr[0] << 32) | ctr[1];
+            const double u1 = ((double)(b >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+            const double u2 = ((double)ctr[2] * 4294967296.0 + (double)ctr[3]) * (1.0 / 18446744073709551616.0);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            z[2 * half] = rad * cs;
+            z[2 * half + 1] = rad * sn;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * gidx + e < count) out[4 * gidx + e] = z[e];
+    }
+}
+
 }  // namespace lq
 
 using namespace lq;
@@ -1175,12 +1217,13 @@ int lq_svd_gram(lq_ctx* h, const double* A, int64_t m, int n, double tol, double
     return LQ_OK;
 }
 // linalg/svd.py:67-76 on the device: orthonormal completion of U (host, m x n, first `rank` columns
-// valid) from the candidate directions Z (host, m x (n - rank), drawn by the caller).
-int lq_svd_complete(lq_ctx* h, double* U, int64_t m, int n, int rank, const double* Z) {
+// valid) from the candidate directions Z: drawn by the caller (host, m x (n - rank): upstream draws them from the global
+// np.random) or, with a seed, generated on the device (no upload; deterministic -- SURVEY.md section 8f-1).
+static int svd_complete_impl(lq_ctx* h, double* U, int64_t m, int n, int rank, const double* Z, bool seeded, unsigned long long seed) {
     Ctx* c = as_ctx(h);
     if (!c) return LQ_ERR_ARG;
     const int k = n - rank;
-    LQ_REQUIRE(c, m >= n && rank >= 0 && k >= 1 && U && Z, LQ_ERR_SHAPE, "svd_complete: bad arguments");
+    LQ_REQUIRE(c, m >= n && rank >= 0 && k >= 1 && U && (Z || seeded), LQ_ERR_SHAPE, "svd_complete: bad arguments");
     LQ_REQUIRE(c, m < (1LL << 31), LQ_ERR_SHAPE, "svd_complete: too many rows");
     LQ_CUDA(c, cudaSetDevice(c->device));
     DevBuf dU, dZ, dQ, dR, dW;
@@ -1190,7 +1233,14 @@ int lq_svd_complete(lq_ctx* h, double* U, int64_t m, int n, int rank, const doub
     LQ_TRY(dR.alloc(c, sizeof(double) * (size_t)k * k));
     LQ_TRY(dW.alloc(c, sizeof(double) * (size_t)n * k));
     LQ_CUDA(c, cudaMemcpyAsync(dU.p, U, sizeof(double) * (size_t)m * n, cudaMemcpyHostToDevice, c->stream));
-    LQ_CUDA(c, cudaMemcpyAsync(dZ.p, Z, sizeof(double) * (size_t)m * k, cudaMemcpyHostToDevice, c->stream));
+    if (seeded) {
+        const long long count = (long long)m * k;
+        philox_normal_kernel<<<grid_for(c, (count + 3) / 4), 256, 0, c->stream>>>(dZ.as<double>(), count, seed);
+        LQ_CHECK_LAUNCH(c);
+        LQ_COUNT_LAUNCH(c);
+    } else {
+        LQ_CUDA(c, cudaMemcpyAsync(dZ.p, Z, sizeof(double) * (size_t)m * k, cudaMemcpyHostToDevice, c->stream));
+    }
     LQ_TRY(lq_householder_qr_dev(h, dZ.as<double>(), (int)m, k, dQ.as<double>(), dR.as<double>()));          // svd.py:69
     if (rank > 0) {
         // Q -= U_r (U_r^T Q)                                                                                // svd.py:71-72
@@ -1202,6 +1252,23 @@ int lq_svd_complete(lq_ctx* h, double* U, int64_t m, int n, int rank, const doub
     LQ_CUDA(c, cudaMemcpy2DAsync(U + rank, sizeof(double) * n, dZ.p, sizeof(double) * k, sizeof(double) * k, (size_t)m,
                                  cudaMemcpyDeviceToHost, c->stream));
     LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LQ_OK;
+}
+int lq_svd_complete(lq_ctx* h, double* U, int64_t m, int n, int rank, const double* Z) {
+    return svd_complete_impl(h, U, m, n, rank, Z, false, 0ULL);
+}
+int lq_svd_complete_seeded(lq_ctx* h, double* U, int64_t m, int n, int rank, uint64_t seed) {
+    return svd_complete_impl(h, U, m, n, rank, nullptr, true, (unsigned long long)seed);
+}
+int lq_random_normal_dev(lq_ctx* h, double* out, int64_t count, uint64_t seed) {
+    Ctx* c = as_ctx(h);
+    if (!c) return LQ_ERR_ARG;
+    LQ_REQUIRE(c, count >= 0 && (count == 0 || out), LQ_ERR_ARG, "random_normal: bad arguments");
+    if (count == 0) return LQ_OK;
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    philox_normal_kernel<<<grid_for(c, (count + 3) / 4), 256, 0, c->stream>>>(out, count, (unsigned long long)seed);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
     return LQ_OK;
 }
 

@@ -12,8 +12,9 @@ import ctypes as C
 import numpy as np
 
 from . import _native as nat
-from .qr import householder_qr
+from .qr import householder_qr, householder_qr_batched, qr, qr_batched
 from .svd import svd
+from .utils import EPS, as_f64_batch, as_f64_matrix
 
 
 def _matmul(ctx, A: np.ndarray, B: np.ndarray, trans_a: bool = False) -> np.ndarray:
@@ -75,3 +76,84 @@ def pca(A, k: int, *, ctx=None):
     total_variance = float(np.sum(S ** 2)) / (n_samples - 1)  # = ||X||_F^2 / (n - 1)
     explained_variance_ratio = explained_variance / total_variance
     return pcs, scores, explained_variance, explained_variance_ratio, total_variance, mean_.ravel()
+
+
+# ----------------------------------------------------------------------------- 8(f)-4: callers of `qr`
+def det_batched(A, *, ctx=None, devices=None) -> np.ndarray:
+    """Determinants of a (batch, n, n) array from the batched Householder factorisation:
+    ``det(A) = det(Q) det(R) = (-1)^k prod(diag R)``, k = number of reflectors actually applied (a column with
+    ``||x|| < 1e-12`` is skipped, linalg/qr.py:79-80, and leaves ``|R[j, j]| < 1e-12``).  A skipped column means the
+    matrix is singular at the reference's own absolute threshold (``qr`` would raise "linearly dependent" on it,
+    linalg/qr.py:40-41): the determinant is then reported as exactly 0, which sends ``adj`` down the cofactor branch
+    like the reference's exact-zero pivots do.  The reference's ``det`` (elimination, out of scope) is only needed by
+    ``adj``; this keeps ``adj`` entirely on the hot path's kernels."""
+    A = as_f64_batch(A)
+    b, m, n = A.shape
+    if m != n:
+        raise ValueError("A must be a square matrix")
+    if n == 0:
+        return np.ones(b)
+    _, R = householder_qr_batched(A, ctx=ctx, devices=devices)
+    d = np.diagonal(R, axis1=1, axis2=2)
+    applied = np.sum(np.abs(d) >= EPS, axis=1)
+    return np.where(applied == n, np.where(n % 2 == 0, 1.0, -1.0) * np.prod(d, axis=1), 0.0)
+
+
+def det(A, *, ctx=None) -> float:
+    A = as_f64_matrix(A)
+    return float(det_batched(A[None], ctx=ctx)[0])
+
+
+def adj_batched(A, *, ctx=None, devices=None) -> np.ndarray:
+    """Adjugate of every ``A[b]`` (linalg/matrix_functions.py:36-63): ``det(A) A^-1`` with ``A^-1 = R^-1 Q^T`` from the
+    MGS ``qr`` for the non-singular matrices, cofactor expansion (determinants of the (n-1) x (n-1) minors, one batched
+    call) for the matrices whose determinant is exactly 0 -- the reference's branch condition ``d == 0`` (:48)."""
+    A = as_f64_batch(A)
+    b, m, n = A.shape
+    if m != n:
+        raise ValueError("A must be a square matrix")
+    out = np.empty_like(A)
+    if b == 0 or n == 0:
+        return out
+    d = det_batched(A, ctx=ctx, devices=devices)
+    sing = d == 0.0
+    idx = np.flatnonzero(~sing)
+    if idx.size:
+        Q, R = qr_batched(A[idx], ctx=ctx, devices=devices)          # matrix_functions.py:61
+        ain = np.linalg.solve(R, np.swapaxes(Q, 1, 2))                # :62 (n x n triangular systems, host LAPACK like upstream)
+        out[idx] = d[idx, None, None] * ain
+    for i in np.flatnonzero(sing):                                    # :49-58
+        if n == 1:
+            out[i] = 1.0
+            continue
+        keep = [np.arange(n) != r for r in range(n)]
+        minors = np.stack([A[i][keep[r]][:, keep[c]] for r in range(n) for c in range(n)])
+        cof = det_batched(minors, ctx=ctx, devices=devices).reshape(n, n)
+        sign = (-1.0) ** np.add.outer(np.arange(n), np.arange(n))
+        out[i] = (sign * cof).T
+    return out
+
+
+def adj(A, *, ctx=None) -> np.ndarray:
+    """Adjugate (classical adjoint) of a square matrix, ``linalg/matrix_functions.py:36-63`` on the device path."""
+    A = np.asarray(A)
+    if A.ndim != 2:
+        raise ValueError("A must be a square matrix")
+    return adj_batched(A.astype(float)[None], ctx=ctx)[0]
+
+
+def random_nonsingular_qr_batched(n: int, seeds, *, ctx=None, devices=None) -> np.ndarray:
+    """``random_nonsingular_qr(n, seed)`` (linalg/qr.py:137-154) for every seed of ``seeds`` in one batched MGS call:
+    matrix i is bitwise what the one-matrix drop-in returns for ``seeds[i]`` and equals the reference's
+    ``random_nonsingular_qr(n, seeds[i])`` to rounding (same ``default_rng`` draws: A first, then the column scales)."""
+    seeds = list(seeds)
+    A = np.empty((len(seeds), n, n))
+    scales = np.empty((len(seeds), n))
+    for i, sd in enumerate(seeds):
+        rng = np.random.default_rng(sd)
+        A[i] = rng.standard_normal((n, n))
+        scales[i] = rng.uniform(0.5, 10.0, size=n)
+    if len(seeds) == 0 or n == 0:
+        return A
+    Q, _ = qr_batched(A, ctx=ctx, devices=devices)
+    return Q * scales[:, None, :]

@@ -26,6 +26,17 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data
 
 
+def _run_batched(ctx, devices, batch, fn):
+    """``fn(ctx, lo, hi)`` on the whole batch with one context, or on contiguous slices of it with one context and one
+    host thread per device of ``devices`` (optional kwarg of the ``*_batched`` entry points)."""
+    if devices is None:
+        fn(_ctx(ctx), 0, batch)
+    else:
+        if ctx is not None:
+            raise ValueError("pass either ctx= or devices=, not both")
+        nat.fan_out(devices, batch, fn)
+
+
 # ----------------------------------------------------------------------------- a1
 def householder_qr(A, *, ctx=None) -> Tuple[np.ndarray, np.ndarray]:
     """Householder QR of an (m, n) matrix, m >= n.  Returns Q (m, n), R (n, n).
@@ -46,8 +57,11 @@ def householder_qr(A, *, ctx=None) -> Tuple[np.ndarray, np.ndarray]:
     return Q, R
 
 
-def householder_qr_batched(A, *, out=None, ctx=None) -> Tuple[np.ndarray, np.ndarray]:
-    """``householder_qr`` applied independently to every ``A[b]`` of a (batch, m, n) array."""
+def householder_qr_batched(A, *, out=None, ctx=None, devices=None) -> Tuple[np.ndarray, np.ndarray]:
+    """``householder_qr`` applied independently to every ``A[b]`` of a (batch, m, n) array.
+
+    ``devices=[0, 1, ...]`` splits the batch index contiguously over several GPUs of this process (no communication);
+    the result is bitwise the one-GPU result."""
     A = as_f64_batch(A)
     b, m, n = A.shape
     if m < n:
@@ -59,7 +73,8 @@ def householder_qr_batched(A, *, out=None, ctx=None) -> Tuple[np.ndarray, np.nda
         _check_out(Q, (b, m, n))
         _check_out(R, (b, n, n))
     if b and m and n:
-        _ctx(ctx).call("lq_householder_qr_batched", _ptr(A), b, m, n, _ptr(Q), _ptr(R))
+        _run_batched(ctx, devices, b, lambda c, lo, hi: c.call("lq_householder_qr_batched", _ptr(A[lo:hi]), hi - lo, m, n,
+                                                               _ptr(Q[lo:hi]), _ptr(R[lo:hi])))
     return Q, R
 
 
@@ -86,7 +101,7 @@ def qr(A, reorth: bool = False, *, ctx=None) -> Tuple[np.ndarray, np.ndarray]:
     return Q, R
 
 
-def qr_batched(A, reorth: bool = False, *, out=None, ctx=None) -> Tuple[np.ndarray, np.ndarray]:
+def qr_batched(A, reorth: bool = False, *, out=None, ctx=None, devices=None) -> Tuple[np.ndarray, np.ndarray]:
     A = as_f64_batch(A)
     b, m, n = A.shape
     if out is None:
@@ -97,7 +112,8 @@ def qr_batched(A, reorth: bool = False, *, out=None, ctx=None) -> Tuple[np.ndarr
         _check_out(R, (b, n, n))
     info = np.zeros(max(b, 1), dtype=np.int32)
     if b and m and n:
-        _ctx(ctx).call("lq_mgs_qr_batched", _ptr(A), b, m, n, int(bool(reorth)), _ptr(Q), _ptr(R), _ptr(info))
+        _run_batched(ctx, devices, b, lambda c, lo, hi: c.call("lq_mgs_qr_batched", _ptr(A[lo:hi]), hi - lo, m, n, int(bool(reorth)),
+                                                               _ptr(Q[lo:hi]), _ptr(R[lo:hi]), _ptr(info[lo:hi])))
     if np.any(info[:b] != 0):
         raise ValueError(_DEPENDENT)
     return Q, R
@@ -147,7 +163,7 @@ def least_squares_qr(A, b, *, ctx=None) -> np.ndarray:
     return X.ravel()
 
 
-def least_squares_householder_qr_batched(A, B, *, out=None, ctx=None) -> np.ndarray:
+def least_squares_householder_qr_batched(A, B, *, out=None, ctx=None, devices=None) -> np.ndarray:
     """A (batch, m, n), B (batch, m, k) -> X (batch, n, k)."""
     A = as_f64_batch(A)
     B = as_f64_batch(B, "B")
@@ -160,11 +176,12 @@ def least_squares_householder_qr_batched(A, B, *, out=None, ctx=None) -> np.ndar
     X = np.empty((bsz, n, k)) if out is None else out
     _check_out(X, (bsz, n, k))
     if bsz and n and k:
-        _ctx(ctx).call("lq_lstsq_householder_batched", _ptr(A), _ptr(B), bsz, m, n, k, _ptr(X))
+        _run_batched(ctx, devices, bsz, lambda c, lo, hi: c.call("lq_lstsq_householder_batched", _ptr(A[lo:hi]), _ptr(B[lo:hi]),
+                                                                 hi - lo, m, n, k, _ptr(X[lo:hi])))
     return X
 
 
-def least_squares_qr_batched(A, B, *, out=None, ctx=None) -> np.ndarray:
+def least_squares_qr_batched(A, B, *, out=None, ctx=None, devices=None) -> np.ndarray:
     """Batched MGS least squares; X has shape (batch, n*k) -- each row is the reference's ravel()."""
     A = as_f64_batch(A)
     B = as_f64_batch(B, "B")
@@ -176,7 +193,9 @@ def least_squares_qr_batched(A, B, *, out=None, ctx=None) -> np.ndarray:
     _check_out(X.reshape(bsz, n, k), (bsz, n, k))
     info = np.zeros(max(bsz, 1), dtype=np.int32)
     if bsz and n and k:
-        _ctx(ctx).call("lq_lstsq_mgs_batched", _ptr(A), _ptr(B), bsz, m, n, k, _ptr(X), _ptr(info))
+        Xv = X.reshape(bsz, n, k)
+        _run_batched(ctx, devices, bsz, lambda c, lo, hi: c.call("lq_lstsq_mgs_batched", _ptr(A[lo:hi]), _ptr(B[lo:hi]), hi - lo, m, n, k,
+                                                                 _ptr(Xv[lo:hi]), _ptr(info[lo:hi])))
     if np.any(info[:bsz] != 0):
         raise ValueError(_DEPENDENT)
     return X.reshape(bsz, n * k)

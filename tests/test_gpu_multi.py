@@ -125,3 +125,32 @@ def test_sharded_tsqr_and_svd_two_ranks(tmp_path):
             so = np.linalg.svd(A, compute_uv=False)
             lead = so > 1e-4 * so[0]
             assert np.max(np.abs(sv[lead] - so[lead]) / so[lead]) <= 1e-6, name
+
+
+def test_devices_kwarg_matches_one_gpu_bitwise():
+    """householder_qr_batched / qr_batched / least_squares_*_batched(devices=[0, 1]): one process, one host thread and one
+    context per GPU, contiguous batch split, no communication -- bitwise the single-GPU result (SURVEY.md sections 5, 8b)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import linalg_b200 as lb
+
+    rng = np.random.default_rng(77)
+    A = rng.standard_normal((4099, 32, 32))
+    Q1, R1 = lb.householder_qr_batched(A)
+    Q2, R2 = lb.householder_qr_batched(A, devices=[0, 1])
+    assert np.array_equal(Q1, Q2) and np.array_equal(R1, R2)
+    Q1, R1 = lb.qr_batched(A)
+    Q2, R2 = lb.qr_batched(A, devices=[1, 0])
+    assert np.array_equal(Q1, Q2) and np.array_equal(R1, R2)
+    A3 = rng.standard_normal((301, 256, 64))
+    B3 = rng.standard_normal((301, 256, 16))
+    X1 = lb.least_squares_householder_qr_batched(A3, B3)
+    X2 = lb.least_squares_householder_qr_batched(A3, B3, devices=[0, 1])
+    assert np.array_equal(X1, X2)
+    assert np.array_equal(lb.least_squares_qr_batched(A3, B3), lb.least_squares_qr_batched(A3, B3, devices=[0, 1]))
+    # the reference's error surfaces from whichever device meets it
+    A[4000, :, 7] = A[4000, :, 3]
+    with pytest.raises(ValueError, match="linearly dependent"):
+        lb.qr_batched(A, devices=[0, 1])
+    with pytest.raises(ValueError):
+        lb.householder_qr_batched(A, devices=[0, 0])

@@ -581,3 +581,67 @@ def test_no_cpu_fallback_loaded(ctx):
     assert ctx.launches() > 0
     maps = open("/proc/self/maps").read()
     assert _native.LIB_PATH in maps
+
+
+# ----------------------------------------------------------------------------- section 8(f): remaining rows
+def test_adjugate_matches_reference_contract(ctx):
+    """tests/test_matrix_functions.py:21-28 (adj vs det * inv, atol 1e-8) for the one-matrix and the batched form, plus the
+    singular branch of linalg/matrix_functions.py:48-58 (cofactors) on an exactly singular matrix."""
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((10, 10))
+    assert np.allclose(lb.adj(A, ctx=ctx), np.linalg.det(A) * np.linalg.inv(A), atol=1e-8)
+    assert np.isclose(lb.det(A, ctx=ctx), np.linalg.det(A), rtol=1e-10)
+    Ab = rng.standard_normal((257, 12, 12))
+    ref = np.linalg.det(Ab)[:, None, None] * np.linalg.inv(Ab)
+    got = lb.adj_batched(Ab, ctx=ctx)
+    assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=(1, 2), keepdims=True)) <= 1e-10
+    assert np.allclose(lb.det_batched(Ab, ctx=ctx), np.linalg.det(Ab), rtol=1e-10)
+    S = np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0], [4.0, 5.0, 6.0]])          # det == 0 exactly: cofactor branch
+    assert lb.det(S, ctx=ctx) == 0.0
+    cof = np.array([[0.0, 3.0, 0.0], [0.0, -6.0, 0.0], [0.0, 3.0, 0.0]])          # hand-computed adjugate
+    assert np.allclose(lb.adj(S, ctx=ctx), cof, atol=1e-12)
+    with pytest.raises(ValueError):
+        lb.adj(np.ones((3, 4)), ctx=ctx)
+
+
+def test_random_nonsingular_qr_batched(ctx):
+    """linalg/qr.py:137-154 for a list of seeds in one batched MGS call: every matrix equals the one-matrix drop-in bitwise
+    and the reference's algorithm (oracle MGS on the same default_rng draws) to rounding; columns orthogonal with the drawn
+    norms, i.e. non-singular -- what tests/test_elimination.py:71-103 relies on."""
+    seeds = [0, 1, 7, 123, 2 ** 31]
+    M = lb.random_nonsingular_qr_batched(9, seeds, ctx=ctx)
+    for i, sd in enumerate(seeds):
+        assert np.array_equal(M[i], lb.random_nonsingular_qr(9, seed=sd, ctx=ctx))
+        rng = np.random.default_rng(sd)
+        A0 = rng.standard_normal((9, 9))
+        Qo, _ = orc.mgs_qr(A0)
+        sc = rng.uniform(0.5, 10.0, size=9)
+        assert orc.rel_max_err(M[i], Qo * sc) <= 1e-10
+        G = M[i].T @ M[i]
+        assert np.allclose(G, np.diag(sc ** 2), atol=1e-10)
+
+
+def test_svd_rank_deficient_device_seeded(ctx):
+    """seed=: the completion of linalg/svd.py:67-76 from device-generated candidates -- deterministic,
+    and the invariants tests/test_svd.py:60-79 pins hold; seed=None keeps the upstream (global np.random) behaviour."""
+    for k in (1, 3):
+        A = np.random.default_rng(123 + k).normal(size=(10, 7))
+        A[:, -k:] = 0.0
+        U1, s1, Vt1 = lb.svd(A, ctx=ctx, seed=42)
+        U2, s2, Vt2 = lb.svd(A, ctx=ctx, seed=42)
+        assert np.array_equal(U1, U2) and np.array_equal(s1, s2)
+        U3, _, _ = lb.svd(A, ctx=ctx, seed=43)
+        assert not np.array_equal(U1[:, -k:], U3[:, -k:])
+        r = 7 - k
+        assert np.all(s1[:r] > 1e-12) and np.all(s1[r:] < 1e-12)
+        assert np.linalg.norm((U1 * s1) @ Vt1 - A) < 1e-10
+        assert np.allclose(U1.T @ U1, np.eye(7), atol=1e-10)
+    # the generator itself: N(0, 1) moments, a function of (seed, index) only
+    n = 1 << 20
+    d1, d2 = ctx.alloc(8 * n), ctx.alloc(8 * (n // 2 + 3))
+    ctx.call("lq_random_normal_dev", d1.ptr, n, 5)
+    ctx.call("lq_random_normal_dev", d2.ptr, n // 2 + 3, 5)
+    z, z2 = ctx.download(d1, (n,)), ctx.download(d2, (n // 2 + 3,))
+    assert np.array_equal(z[: n // 2 + 3], z2)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3 and abs(np.mean(z ** 4) - 3.0) < 5e-2
+    assert np.all(np.isfinite(z)) and len(np.unique(z)) > 0.999 * n

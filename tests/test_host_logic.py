@@ -140,3 +140,34 @@ def test_control_plane_gloo_world2(tmp_path):
         assert np.array_equal(z["Q"], Qo[lo:hi]) and np.array_equal(z["R"], Ro[lo:hi])
         seen[lo:hi] = True
     assert seen.all()
+
+
+def test_fan_out_splits_contiguously_and_reraises():
+    """devices= plumbing of the *_batched entry points (no GPU: fake contexts)."""
+    import threading
+
+    from linalg_b200 import _native as nat
+
+    seen, lock = [], threading.Lock()
+
+    def fn(ctx, lo, hi):
+        with lock:
+            seen.append((ctx, lo, hi, threading.current_thread().name))
+
+    nat.fan_out([3, 5, 6], 10, fn, _contexts=["c3", "c5", "c6"])
+    assert sorted((c, lo, hi) for c, lo, hi, _ in seen) == [("c3", 0, 4), ("c5", 4, 7), ("c6", 7, 10)]
+    assert len({name for *_, name in seen}) == 3            # one host thread per device
+    seen.clear()
+    nat.fan_out([0, 1, 2, 3], 2, fn, _contexts="abcd")      # more devices than units: empty slices are skipped
+    assert sorted((lo, hi) for _, lo, hi, _ in seen) == [(0, 1), (1, 2)]
+
+    def boom(ctx, lo, hi):
+        if ctx == "b":
+            raise ValueError("Input vectors are linearly dependent")
+
+    with pytest.raises(ValueError, match="linearly dependent"):
+        nat.fan_out([0, 1], 8, boom, _contexts="ab")
+    with pytest.raises(ValueError):
+        nat.fan_out([1, 1], 8, fn, _contexts="ab")
+    with pytest.raises(ValueError):
+        nat.fan_out([], 8, fn)
