@@ -408,6 +408,30 @@ def main():
            "d2h_bytes_per_step": int(hQ.nbytes + hR.nbytes), "steps": e2e_steps, "batch_per_gpu": e2e_batch,
            "pcie_gbs": (hA.nbytes + hQ.nbytes + hR.nbytes) * e2e_steps / e2e_s / 1e9,
            "api": "lq_householder_qr_batched (host pointers, pinned NumPy buffers)"}
+    # the host side's ceiling for this call: the same bytes (A up, Q and R down) as plain cudaMemcpyAsync copies from / to the
+    # same pinned buffers, H2D and D2H on two streams, all ranks at once -- no kernels.  e2e / ceiling says how much of the
+    # copy roof the pipeline reaches; ceiling(N) / ceiling(1) says what the box's host memory / PCIe fabric gives N GPUs.
+    try:
+        nb = min(e2e_batch, batch) * N32 * N32 * 8
+        ctx2 = lb.Context(ctx.device)
+        best = None
+        for _ in range(3):
+            ctx.sync(); ctx2.sync()
+            d.barrier()
+            t0 = time.perf_counter()
+            ctx.call("lq_memcpy_h2d", dA.ptr, hA.ctypes.data, nb)
+            ctx2.call("lq_memcpy_d2h", hQ.ctypes.data, dQ.ptr, nb)
+            ctx2.call("lq_memcpy_d2h", hR.ctypes.data, dR.ptr, nb)
+            ctx.sync(); ctx2.sync()
+            dt = d.max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        ceil_gbs = info.world * 3 * nb / best / 1e9
+        e2e["copy_ceiling"] = {"all_ranks_gbs": ceil_gbs, "per_gpu_gbs": ceil_gbs / info.world,
+                               "e2e_frac_of_ceiling": e2e["pcie_gbs"] * info.world / ceil_gbs,
+                               "how": "cudaMemcpyAsync of A (H2D) and Q, R (D2H) on two streams from the same pinned buffers, all ranks concurrently, best of 3"}
+        ctx2.close()
+    except Exception as exc:  # diagnostics only
+        e2e["copy_ceiling"] = {"error": repr(exc)}
     del hA, hQ, hR
     dA.free(); dQ.free(); dR.free()
 
@@ -639,13 +663,13 @@ def run_extras(ctx, d, info, peaks):
         rk = C.c_int(0)
         ms = timed(ctx, lambda: ctx.call("lq_svd_gram" + sh + "_dev", dA.ptr, m, n, C.c_double(1e-12), dU.ptr, ds.ptr, dVt.ptr, C.byref(rk)), 5, 2)
         t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
-        f_svd = 2.0 * 2.0 * m * n * n      # Gram (full GEMM count) + U = A V S^-1
+        f_svd = 3.0 * m * n * n            # Gram as a symmetric rank-k update (m n^2) + U = A V S^-1 (2 m n^2)
         out["cfg5_svd_gram" + tag] = {"rows_total": m * info.world, "rows_per_gpu": m, "ms": t * 1e3, "gflops": info.world * f_svd / t / 1e9,
                                       "fp64_frac": f_svd / t / 1e12 / peak64, "rank": rk.value,
                                       "collective": "ncclAllReduce 128x128 f64" if info.world > 1 else None}
         ms = timed(ctx, lambda: ctx.call("lq_tsqr" + sh + "_dev", dA.ptr, m, n, dQ.ptr, dR.ptr), 5, 2)
         t = d.max_over_ranks(statistics.mean(ms)) * 1e-3
-        executed = 4 * 2.0 * m * n * n  # CholeskyQR2: two Gram products + two triangular-inverse products
+        executed = 6.0 * m * n * n      # CholeskyQR2: two SYRK Gram products (m n^2 each) + two A R^-1 products (2 m n^2 each)
         algorithmic = 4.0 * m * n * n   # Householder-equivalent: factor (2 m n^2) + explicit Q (2 m n^2)
         out["cfg5_tsqr" + tag] = {"rows_total": m * info.world, "rows_per_gpu": m, "ms": t * 1e3,
                                   "gflops_householder_equiv": info.world * algorithmic / t / 1e9,

@@ -87,9 +87,9 @@ static int launch_hh32_ll(Ctx* c, cudaStream_t st, const double* A, long long ba
 }
 
 // lane = column, four matrices per warp, left-looking panels + DMMA Q phase
-template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false>
+template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false>
 static int launch_hh32_c8(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
-    auto kern = hh_qr32_c8_kernel<WARPS, MINB, PHASES, KEEPV>;
+    auto kern = hh_qr32_c8_kernel<WARPS, MINB, PHASES, KEEPV, PF>;
     const size_t smem = (size_t)WARPS * Col8::WARP_DOUBLES * sizeof(double);
     static DeviceLatch configured;
     if (!configured.test(c->device)) {
@@ -153,9 +153,9 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 57: return launch_hh32_c8<2, 5, 1, true>(c, st, A, batch, Q, R);
             case 58: return launch_hh32_c8<4, 2, 3, true>(c, st, A, batch, Q, R);
             case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
-            case 64: return launch_hh32_c8<9, 1, 3, true>(c, st, A, batch, Q, R);
-            case 65: return launch_hh32_c8<9, 1, 3, false>(c, st, A, batch, Q, R);
-            case 66: return launch_hh32_c8<7, 1, 3, true>(c, st, A, batch, Q, R);
+            case 64: return launch_hh32_c8<8, 1, 3, true, true>(c, st, A, batch, Q, R);   // + L2 prefetch of the later panels
+            case 65: return launch_hh32_c8<8, 1, 3, false, true>(c, st, A, batch, Q, R);
+            case 66: return launch_hh32_c8<4, 2, 3, true, true>(c, st, A, batch, Q, R);
             case 61: return launch_hh32_c8<4, 2, 1, true>(c, st, A, batch, Q, R);
             case 62: return launch_hh32_c8<4, 2, 1, false>(c, st, A, batch, Q, R);
             case 63: return launch_hh32_c8<4, 2, 2, false>(c, st, A, batch, Q, R);

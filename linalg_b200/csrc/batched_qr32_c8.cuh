@@ -53,7 +53,7 @@ __device__ __forceinline__ double2 lds128v(const double* p) {
 
 // PHASES: 3 = product; 1 = R phase only, 2 = Q phase only (timing diagnostics).  KEEPV: keep the broadcast reflector in
 // registers between dot product and update instead of re-reading it.
-template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false>
+template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     hh_qr32_c8_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, long long batch) {
     constexpr int N = 32;
@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         double* vb = wbase + g4 * Col8::MAT;
         double* betas = vb + Col8::BETA;
 
+        if (PF) {
+            // the later panels of my four matrices: pull their lines into L2 now (a row is two 128-byte lines, panel 0 only
+            // brings the first half of the first one); 256 lines per warp = 8 prefetches per lane
+            const double* base = A + mat0 * (N * N);
+            const long long last = (batch - mat0) * (N * N) * 8 - 1;  // bytes of valid input behind base, minus one
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const long long off = ((long long)q * 32 + lane) * 128;
+                if (off <= last) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
+            }
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int col = 8 * p + c;

@@ -83,6 +83,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     for (int r0 = 0; r0 < m; r0 += L::ROWS) {
         // ---- the next 32 rows of [A | B] as transposed accumulator tiles
         double ct[NCB + NRT][RB][2];
+        if (r0 + L::ROWS < m) {
+            // the block after this one: into L2 now, so that its loads are short-latency hits when the panel loop is done
+            const long long a0 = (long long)(r0 + L::ROWS) * n * 8, a1 = min((long long)(r0 + 2 * L::ROWS), (long long)m) * n * 8;
+            for (long long off = a0 + (long long)lane * 128; off < a1; off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Ag) + off));
+            const long long b0 = (long long)(r0 + L::ROWS) * nrhs * 8, b1 = min((long long)(r0 + 2 * L::ROWS), (long long)m) * nrhs * 8;
+            for (long long off = b0 + (long long)lane * 128; off < b1; off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Bg) + off));
+        }
         if (full_cols && r0 + L::ROWS <= m) {
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb)
