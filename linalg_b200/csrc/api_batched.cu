@@ -127,6 +127,12 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 59: return launch_hh32_c8<8, 1, 3, true>(c, st, A, batch, Q, R);
             case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // round-1 default: reciprocal seeded from the raw rsqrt
             case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
+            case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
+            case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
+            case 52: return launch_hh32_c8<4, 2>(c, st, A, batch, Q, R);
+            case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
+            case 36: return launch_hh32_ll<2, 4, 3, 3, true>(c, st, A, batch, Q, R);
+#ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
             case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
             case 2: return launch_hh32<1, 2, 4, false, 2>(c, st, A, batch, Q, R);
@@ -138,21 +144,17 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 10: return launch_hh32<4, 4, 4, false, 5>(c, st, A, batch, Q, R);
             case 11: return launch_hh32<2, 2, 4, true, 3>(c, st, A, batch, Q, R);
             case 12: return launch_hh32<4, 4, 2, true, 8, 2>(c, st, A, batch, Q, R);
-            case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
             case 20: return launch_hh32_dmma<2, 4>(c, st, A, batch, Q, R);
-            case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
             case 22: return launch_hh32_dmma<1, 8>(c, st, A, batch, Q, R);
             case 23: return launch_hh32_dmma<4, 2, 1>(c, st, A, batch, Q, R);
             case 50: return launch_hh32_c8<2, 5>(c, st, A, batch, Q, R);
             case 51: return launch_hh32_c8<2, 4>(c, st, A, batch, Q, R);
-            case 52: return launch_hh32_c8<4, 2>(c, st, A, batch, Q, R);
             case 53: return launch_hh32_c8<2, 5, 1>(c, st, A, batch, Q, R);
             case 54: return launch_hh32_c8<2, 5, 2>(c, st, A, batch, Q, R);
             case 55: return launch_hh32_c8<2, 5, 3, true>(c, st, A, batch, Q, R);
             case 56: return launch_hh32_c8<2, 4, 3, true>(c, st, A, batch, Q, R);
             case 57: return launch_hh32_c8<2, 5, 1, true>(c, st, A, batch, Q, R);
             case 58: return launch_hh32_c8<4, 2, 3, true>(c, st, A, batch, Q, R);
-            case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
             case 64: return launch_hh32_c8<8, 1, 3, true, true>(c, st, A, batch, Q, R);   // + L2 prefetch of the later panels
             case 65: return launch_hh32_c8<8, 1, 3, false, true>(c, st, A, batch, Q, R);
             case 66: return launch_hh32_c8<4, 2, 3, true, true>(c, st, A, batch, Q, R);
@@ -162,16 +164,17 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 30: return launch_hh32_ll<2, 4, 4>(c, st, A, batch, Q, R);
             case 32: return launch_hh32_ll<2, 4, 4, 1>(c, st, A, batch, Q, R);
             case 34: return launch_hh32_ll<2, 4, 3>(c, st, A, batch, Q, R);
-            case 36: return launch_hh32_ll<2, 4, 3, 3, true>(c, st, A, batch, Q, R);
             case 37: return launch_hh32_ll<2, 4, 3, 1, true>(c, st, A, batch, Q, R);
             case 38: return launch_hh32_ll<1, 4, 2, 3, true>(c, st, A, batch, Q, R);
             case 39: return launch_hh32_ll<1, 4, 2, 1, true>(c, st, A, batch, Q, R);
             case 40: return launch_hh32_ll<2, 4, 4, 2>(c, st, A, batch, Q, R);
             case 41: return launch_hh32_ll<2, 2, 6, 3, true>(c, st, A, batch, Q, R);
             case 24: return launch_hh32_dmma<4, 2, 2>(c, st, A, batch, Q, R);
+#endif
             default: break;
         }
-        set_error(c, "householder_qr_batched: unknown kernel variant %d", variant);
+        set_error(c, "householder_qr_batched: unknown kernel variant %d (the design-space variants need a library built with "
+                     "LINALG_B200_ALL_VARIANTS=1)", variant);
         return LQ_ERR_ARG;
     }
     const size_t smem = small_hh_smem_doubles(m, n, 0) * sizeof(double);
