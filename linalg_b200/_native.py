@@ -53,6 +53,8 @@ SIGNATURES = {
     "lq_mgs_qr": (C.c_int, [_CTX, _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_void_p]),
     "lq_lstsq_householder_batched_dev": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP]),
     "lq_lstsq_householder_batched": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP]),
+    "lq_lstsq_householder_batched_info": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP, _DP]),
+    "lq_lstsq_householder_batched_info_dev": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP, _DP]),
     "lq_lstsq_mgs_batched_dev": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP, C.c_void_p]),
     "lq_lstsq_mgs_batched": (C.c_int, [_CTX, _DP, _DP, C.c_int64, C.c_int, C.c_int, C.c_int, _DP, C.c_void_p]),
     "lq_svd_gram_dev": (C.c_int, [_CTX, _DP, C.c_int64, C.c_int, C.c_double, _DP, _DP, _DP, C.POINTER(C.c_int)]),

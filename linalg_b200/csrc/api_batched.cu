@@ -221,11 +221,15 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
     return LQ_OK;
 }
 
+// info (device, may be null): per system 0, or 1 + the first column whose R[j][j] is exactly 0 (np.linalg.solve raises
+// LinAlgError("Singular matrix") there, linalg/qr.py:134); reported by the warp-per-system kernel (n <= 64, nrhs <= 16),
+// 0 for the other shapes
 int lstsq_hh_batched_stream(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n,
-                            int nrhs, double* X) {
+                            int nrhs, double* X, int* info = nullptr) {
     if (batch == 0) return LQ_OK;
-    int rc = lstsq_tile_kernel_launch(c, st, A, B, batch, m, n, nrhs, X, nullptr, 0);
+    int rc = lstsq_tile_kernel_launch(c, st, A, B, batch, m, n, nrhs, X, info, 2);
     if (rc != LQ_ERR_UNSUPPORTED) return rc;
+    if (info) LQ_CUDA(c, cudaMemsetAsync(info, 0, sizeof(int) * (size_t)batch, st));
     rc = lstsq_stream_kernel_launch(c, st, A, B, batch, m, n, nrhs, X);
     if (rc != LQ_ERR_UNSUPPORTED) return rc;
     const size_t smem = small_hh_smem_doubles(m, n, nrhs) * sizeof(double);
@@ -396,8 +400,30 @@ int lq_lstsq_householder_batched_dev(lq_ctx* h, const double* A, const double* B
     return lstsq_hh_batched_stream(c, c->stream, A, B, batch, m, n, nrhs, X);
 }
 
+int lq_lstsq_householder_batched_info_dev(lq_ctx* h, const double* A, const double* B, int64_t batch, int m, int n,
+                                          int nrhs, double* X, int32_t* info) {
+    Ctx* c = as_ctx(h);
+    LQ_ARGS_QR(c, A, batch, m, n);
+    LQ_REQUIRE(c, m >= n && nrhs >= 1, LQ_ERR_SHAPE, "least squares needs m >= n and nrhs >= 1 (got %d x %d, %d rhs)", m,
+               n, nrhs);
+    LQ_CUDA(c, cudaSetDevice(c->device));
+    return lstsq_hh_batched_stream(c, c->stream, A, B, batch, m, n, nrhs, X, info);
+}
+
+static int lstsq_hh_host(lq_ctx* h, const double* A, const double* B, int64_t batch, int m, int n, int nrhs, double* X,
+                         int32_t* info);
+
 int lq_lstsq_householder_batched(lq_ctx* h, const double* A, const double* B, int64_t batch, int m, int n, int nrhs,
                                  double* X) {
+    return lstsq_hh_host(h, A, B, batch, m, n, nrhs, X, nullptr);
+}
+int lq_lstsq_householder_batched_info(lq_ctx* h, const double* A, const double* B, int64_t batch, int m, int n, int nrhs,
+                                      double* X, int32_t* info) {
+    return lstsq_hh_host(h, A, B, batch, m, n, nrhs, X, info);
+}
+
+static int lstsq_hh_host(lq_ctx* h, const double* A, const double* B, int64_t batch, int m, int n, int nrhs, double* X,
+                         int32_t* info) {
     Ctx* c = as_ctx(h);
     LQ_ARGS_QR(c, A, batch, m, n);
     LQ_REQUIRE(c, m >= n && nrhs >= 1, LQ_ERR_SHAPE, "least squares needs m >= n and nrhs >= 1 (got %d x %d, %d rhs)", m,
@@ -416,13 +442,14 @@ int lq_lstsq_householder_batched(lq_ctx* h, const double* A, const double* B, in
             LQ_TRY(large_lstsq_householder(c, dA.as<double>(), dB.as<double>(), m, n, nrhs, dX.as<double>()));
             LQ_CUDA(c, cudaMemcpyAsync(X + b * (size_t)n * nrhs, dX.p, nk, cudaMemcpyDeviceToHost, c->stream));
             LQ_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (info) info[b] = 0;
         }
         return LQ_OK;
     }
-    return run_chunked(c, batch, mn, mk, nk, 0, 0, A, B, X, nullptr, nullptr,
-                       [&](cudaStream_t st, long long cnt, void* dA, void* dB, void* dX, void*, void*) {
+    return run_chunked(c, batch, mn, mk, nk, 0, info ? sizeof(int32_t) : 0, A, B, X, nullptr, info,
+                       [&](cudaStream_t st, long long cnt, void* dA, void* dB, void* dX, void*, void* dI) {
                            return lstsq_hh_batched_stream(c, st, (const double*)dA, (const double*)dB, cnt, m, n, nrhs,
-                                                          (double*)dX);
+                                                          (double*)dX, info ? (int*)dI : nullptr);
                        });
 }
 

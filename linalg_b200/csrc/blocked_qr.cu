@@ -384,8 +384,11 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
     cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1], s_merge = c->lane[2], s_side2 = c->lane[3];
     const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
-    DevBuf Tloc, G, W, W2, Ws, W2s, W2s2;
+    // Gram scratch of the T merge: one buffer per stream that may run a merge (main: blocks without panel-wise look-ahead,
+    // e.g. the last one; merge stream: all the others) -- the two streams are not ordered against each other
+    DevBuf Tloc, G, Gmerge, W, W2, Ws, W2s, W2s2;
     LQ_TRY(G.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
+    LQ_TRY(Gmerge.alloc(c, sizeof(double) * NB_OUT * NB_OUT));
     const int wcols = std::max(npad, nrhs_pad);
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
@@ -486,17 +489,17 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
         }
         const double* Vb = V + (size_t)k0 * ldv + k0;
         // the T factor of the whole outer block: on the stream that needs it first
-        auto merge_block_t = [&]() -> int {
+        auto merge_block_t = [&](double* Gs) -> int {
             if (nin <= 1) return LQ_OK;
-            LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, G.as<double>(), NB_OUT));  // G = V^T V
-            if (kb == 128) merge_t_kernel<128><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
-            else merge_t_kernel<0><<<1, 1024, MERGE_T_SMEM, c->stream>>>(G.as<double>(), NB_OUT, Tblk, NB_OUT, kb);
+            LQ_TRY(gemm(c, true, false, kb, kb, mk, 1.0, Vb, ldv, Vb, ldv, 0.0, Gs, NB_OUT));  // G = V^T V
+            if (kb == 128) merge_t_kernel<128><<<1, 1024, MERGE_T_SMEM, c->stream>>>(Gs, NB_OUT, Tblk, NB_OUT, kb);
+            else merge_t_kernel<0><<<1, 1024, MERGE_T_SMEM, c->stream>>>(Gs, NB_OUT, Tblk, NB_OUT, kb);
             LQ_CHECK_LAUNCH(c);
             LQ_COUNT_LAUNCH(c);
             return LQ_OK;
         };
         if (!lookahead) {
-            LQ_TRY(merge_block_t());
+            LQ_TRY(merge_block_t(G.as<double>()));
             if (ntr > 0)
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, ntr, W.as<double>(),
                                              W2.as<double>()));
@@ -513,7 +516,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             // the next block's columns are complete once the aux stream has applied the last panel
             LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_aux_done, 0));
         } else {
-            LQ_TRY(merge_block_t());
+            LQ_TRY(merge_block_t(G.as<double>()));
             if (nnext > 0) {
                 if (ev_rest_prev) LQ_CUDA(c, cudaStreamWaitEvent(s_main, ev_rest_prev, 0));
                 LQ_TRY(apply_block_reflector(c, Vb, ldv, Tblk, NB_OUT, true, mk, kb, Ctr, lda, nnext, W.as<double>(),
@@ -532,7 +535,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
             if (pw) {
                 StreamScope mg(c, s_merge);
                 LQ_CUDA(c, cudaStreamWaitEvent(s_merge, ev_panel, 0));
-                LQ_TRY(merge_block_t());
+                LQ_TRY(merge_block_t(Gmerge.as<double>()));
                 LQ_CUDA(c, cudaEventRecord(ev_after, s_merge));
             } else {
                 LQ_CUDA(c, cudaEventRecord(ev_after, s_main));  // T merged on the main stream

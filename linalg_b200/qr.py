@@ -142,8 +142,11 @@ def least_squares_householder_qr(A, b, *, ctx=None) -> np.ndarray:
     B, was_vec = _rhs_2d(b, m)
     k = B.shape[1]
     X = np.empty((n, k))
+    info = np.zeros(1, dtype=np.int32)
     if n and k:
-        _ctx(ctx).call("lq_lstsq_householder_batched", _ptr(A), _ptr(B), 1, m, n, k, _ptr(X))
+        _ctx(ctx).call("lq_lstsq_householder_batched_info", _ptr(A), _ptr(B), 1, m, n, k, _ptr(X), _ptr(info))
+    if info[0] != 0:
+        raise np.linalg.LinAlgError("Singular matrix")  # np.linalg.solve(R, y) upstream, linalg/qr.py:134
     return X.reshape(n) if was_vec else X
 
 
@@ -175,9 +178,12 @@ def least_squares_householder_qr_batched(A, B, *, out=None, ctx=None, devices=No
     k = B.shape[2]
     X = np.empty((bsz, n, k)) if out is None else out
     _check_out(X, (bsz, n, k))
+    info = np.zeros(max(bsz, 1), dtype=np.int32)
     if bsz and n and k:
-        _run_batched(ctx, devices, bsz, lambda c, lo, hi: c.call("lq_lstsq_householder_batched", _ptr(A[lo:hi]), _ptr(B[lo:hi]),
-                                                                 hi - lo, m, n, k, _ptr(X[lo:hi])))
+        _run_batched(ctx, devices, bsz, lambda c, lo, hi: c.call("lq_lstsq_householder_batched_info", _ptr(A[lo:hi]), _ptr(B[lo:hi]),
+                                                                 hi - lo, m, n, k, _ptr(X[lo:hi]), _ptr(info[lo:hi])))
+    if np.any(info[:bsz] != 0):
+        raise np.linalg.LinAlgError("Singular matrix")  # np.linalg.solve(R, y) upstream, linalg/qr.py:134
     return X
 
 

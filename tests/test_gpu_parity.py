@@ -645,3 +645,23 @@ def test_svd_rank_deficient_device_seeded(ctx):
     assert np.array_equal(z[: n // 2 + 3], z2)
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3 and abs(np.mean(z ** 4) - 3.0) < 5e-2
     assert np.all(np.isfinite(z)) and len(np.unique(z)) > 0.999 * n
+
+
+def test_least_squares_householder_singular_raises_like_numpy(ctx):
+    """A zero column leaves R[j, j] exactly 0; the reference's np.linalg.solve(R, Q^T b) (linalg/qr.py:134) raises
+    LinAlgError("Singular matrix") there -- so do the drop-in entry points, one-matrix and batched."""
+    rng = np.random.default_rng(31)
+    A = rng.standard_normal((40, 6))
+    A[:, 2] = 0.0
+    b = rng.standard_normal(40)
+    with pytest.raises(np.linalg.LinAlgError):
+        orc.lstsq_householder(A, b)
+    with pytest.raises(np.linalg.LinAlgError):
+        lb.least_squares_householder_qr(A, b, ctx=ctx)
+    Ab = rng.standard_normal((9, 256, 64))
+    Bb = rng.standard_normal((9, 256, 16))
+    X = lb.least_squares_householder_qr_batched(Ab, Bb, ctx=ctx)          # regular batch: no report
+    assert orc.rel_max_err(X, orc.lstsq_householder_batched(Ab, Bb)) <= REL
+    Ab[7, :, 63] = 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        lb.least_squares_householder_qr_batched(Ab, Bb, ctx=ctx)
