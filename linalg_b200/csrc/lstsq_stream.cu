@@ -73,9 +73,9 @@ int lstsq_tile_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const dou
     if (!lstsq_tile_kernel_supported(m, n, nrhs)) return LQ_ERR_UNSUPPORTED;
     static const int variant = getenv("LINALG_B200_LSTSQ_TILE_VARIANT") ? atoi(getenv("LINALG_B200_LSTSQ_TILE_VARIANT")) : 0;
     switch (variant) {
-        case 1: return launch_tile<1, 7>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
-        case 2: return launch_tile<3, 2>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
-        default: return launch_tile<7, 1>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
+        case 1: return launch_tile<7, 1>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
+        case 2: return launch_tile<8, 1>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
+        default: return launch_tile<4, 2>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);  // two 4-warp CTAs per SM: 17.4 ms (8 x 1: 17.8, 7 x 1: 19.9)
     }
 }
 

@@ -20,9 +20,10 @@
 //   * columns are factored 8 at a time (a panel): the scalar chain of a column step touches 8 columns instead of 80, and
 //     there is no block-wide barrier anywhere -- a warp only ever synchronises with itself;
 //   * T comes from the Gram matrix X^T X (the top parts of the reflectors are disjoint unit vectors and do not
-//     contribute off the diagonal), 8 DMMA + one 8-step recurrence.
-// R^T (36 upper-triangular tiles), the 64 x 16 right-hand-side rows (16 tiles) and 3 KB of scratch live in shared memory:
-// 30.1 KB per warp, 7 warps per SM.
+//     contribute off the diagonal); its column k falls out of column step k's dot products and is consumed during
+//     step k + 1, off the critical chain.
+// R^T (36 upper-triangular tiles), the 64 x 16 right-hand-side rows (16 tiles) and 2.2 KB of scratch live in shared memory:
+// 28.9 KB per warp, 8 warps per SM (the register file allows no more at 255 registers: a 32 x 80 block is 160 of them).
 #pragma once
 
 #include <type_traits>
@@ -40,12 +41,14 @@ struct LsTile {
     __host__ __device__ static constexpr int tile(int cb, int p) { return 8 * p - (p * (p - 1)) / 2 + (cb - p); }
     static constexpr int A_TILES = 36;
     static constexpr int Y_TILE0 = A_TILES;                 // y tile (rt, p) at Y_TILE0 + 8 * rt + p
-    static constexpr int XS = (A_TILES + 8 * NRT) * 64;     // 32 rows x stride 10: the panel's reflectors, row-major
-    static constexpr int XS_STRIDE = 10;                    // (also the scratch of the back-substitution)
-    static constexpr int TS = XS + ROWS * XS_STRIDE;        // 64: -T
-    static constexpr int GS = TS + 64;                      // 2 x 8: column k of the Gram matrix X^T X (double buffered)
+    static constexpr int XS = (A_TILES + 8 * NRT) * 64;     // 32 rows x 8: the panel's reflectors, row-major, XOR-swizzled
+                                                            // (element (r, c) at 8 r + (c ^ 2 ((r >> 1) & 3)): the column
+                                                            // publishes / reads and the 128-bit row reads are conflict free);
+                                                            // its first 64 doubles are reused for -T once X^T is in registers,
+                                                            // and as the scratch of the back-substitution
+    static constexpr int GS = XS + ROWS * 8;                // 2 x 8: column k of the Gram matrix X^T X (double buffered)
     static constexpr int DV = GS + 16;                      // 8: v0 of the panel's reflectors
-    static constexpr int WARP_DOUBLES = DV + 8;
+    static constexpr int WARP_DOUBLES = DV + 8;             // 3608 doubles = 28 864 B: eight warps per SM
 };
 static_assert(LsTile::tile(7, 7) == 35, "packed triangle");
 
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     lstsq_tile_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ X, int* __restrict__ info,
                       long long batch, int m, int n, int nrhs, int info_mode) {
     using L = LsTile;
-    constexpr int NCB = L::NCB, NRT = L::NRT, RB = L::RB, XSTR = L::XS_STRIDE;
+    constexpr int NCB = L::NCB, NRT = L::NRT, RB = L::RB;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
     double* Rt = sm + (size_t)warp * L::WARP_DOUBLES;
     double* Xs = Rt + L::XS;
-    double* Ts = Rt + L::TS;
+    double* Ts = Xs;  // aliased: written only after the panel's X^T operands have been loaded
     double* Gs = Rt + L::GS;
     double* Dv = Rt + L::DV;
 
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     for (int rb = 0; rb < RB; ++rb) P[rb][0] = ct[cb][rb][0], P[rb][1] = ct[cb][rb][1];
                 }
             double* rpp = Rt + L::tile(p, p) * 64;  // diagonal tile of R^T: [c][i] = R[8p + i][8p + c]
-            double* xrow = Xs + (2 * t) * XSTR;     // + 8 rb XSTR (+ XSTR): rows 8 rb + 2 t (+ 1) of the published reflectors
+            double* xrow = Xs + (2 * t) * 8;        // + 64 rb (+ 8): rows 8 rb + 2 t (+ 1) of the published reflectors; their swizzle is 2 t
 
             // ---- factor the 8 columns of [R_pp ; P].  T (dlarft, forward / columnwise) is built on the way, off the
             // critical chain: column k of the Gram matrix X^T X falls out of step k's dot products (lanes g < k), is
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 if (g == j) {
 #pragma unroll
                     for (int rb = 0; rb < RB; ++rb) {
-                        xrow[8 * rb * XSTR + j] = P[rb][0];
-                        xrow[(8 * rb + 1) * XSTR + j] = P[rb][1];
+                        xrow[64 * rb + (j ^ (2 * t))] = P[rb][0];
+                        xrow[64 * rb + 8 + (j ^ (2 * t))] = P[rb][1];
                     }
                 }
                 const double rjc = rpp[g * 8 + j];  // R[j][c = g]
@@ -154,8 +157,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 double d0 = 0.0, d1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
-                    xk[rb][0] = xrow[8 * rb * XSTR + j];
-                    xk[rb][1] = xrow[(8 * rb + 1) * XSTR + j];
+                    xk[rb][0] = xrow[64 * rb + (j ^ (2 * t))];
+                    xk[rb][1] = xrow[64 * rb + 8 + (j ^ (2 * t))];
                     d0 = fma(xk[rb][0], P[rb][0], d0);
                     d1 = fma(xk[rb][1], P[rb][1], d1);
                     q0 = fma(xk[rb][0], xk[rb][0], q0);
@@ -217,8 +220,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     P[rb][1] = fma(-s, xk[rb][1], P[rb][1]);
                 }
             }
-            // last column of T, then -T row g to shared memory (B operands need it transposed)
+            // X^T operands of the update (row 8 rb + g, columns 2 t, 2 t + 1), the last column of T, then -T row g to shared
+            // memory (B operands need it transposed) -- into the space of X, which is in registers by then
             __syncwarp();
+            double2 Xt[RB];
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb)
+                Xt[rb] = *reinterpret_cast<const double2*>(Xs + (8 * rb + g) * 8 + ((2 * t) ^ (2 * ((g >> 1) & 3))));
+            const double2 d2 = *reinterpret_cast<const double2*>(Dv + 2 * t);
             {
                 const double* gk = Gs + 8;
                 double a0 = 0.0, a1 = 0.0;
@@ -229,17 +238,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 }
                 const double sel = (g == 7) ? 1.0 : 0.0, lt = (g < 7) ? 1.0 : 0.0;
                 Trow[7] = beta_prev * fma(-lt, a0 + a1, sel);
-                if (t == 0) {
+            }
+            __syncwarp();  // every lane holds its X^T operands: the space takes -T
+            if (t == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Ts + g * 8 + k) = make_double2(-Trow[k], -Trow[k + 1]);
-                }
+                for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(Ts + g * 8 + k) = make_double2(-Trow[k], -Trow[k + 1]);
             }
             __syncwarp();
             const double nT0 = Ts[(2 * t) * 8 + g], nT1 = Ts[(2 * t + 1) * 8 + g];
-            const double2 d2 = *reinterpret_cast<const double2*>(Dv + 2 * t);
-            double2 Xt[RB];
-#pragma unroll
-            for (int rb = 0; rb < RB; ++rb) Xt[rb] = *reinterpret_cast<const double2*>(Xs + (8 * rb + g) * XSTR + 2 * t);
 
             // ---- block reflector on the trailing column blocks and the right-hand sides, up to three tiles at a time (the
             // accumulator chains of the tiles of a group interleave; NT is a compile-time count, so a group never
