@@ -7,6 +7,7 @@
 #include "batched_qr32_dmma.cuh"
 #include "batched_qr32_ll.cuh"
 #include "batched_qr32_c8.cuh"
+#include "batched_mgs32_c8.cuh"
 #include "batched_small.cuh"
 #include "ctx.cuh"
 #include "ops.cuh"
@@ -118,6 +119,24 @@ static int launch_mgs32(Ctx* c, cudaStream_t st, const double* A, long long batc
     return LQ_OK;
 }
 
+// lane = column MGS (round 2): four matrices per warp, seven warps per SM
+template <int WARPS, int MINB, bool KEEPV>
+static int launch_mgs32_c8(Ctx* c, cudaStream_t st, const double* A, long long batch, int reorth, double* Q, double* R, int* info) {
+    auto kern = mgs_qr32_c8_kernel<WARPS, MINB, KEEPV>;
+    const size_t smem = (size_t)WARPS * MgsCol8::WARP_DOUBLES * sizeof(double);
+    static DeviceLatch configured;
+    if (!configured.test(c->device)) {
+        LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set(c->device);
+    }
+    const long long per_block = (long long)WARPS * 4;
+    const long long blocks = (batch + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, Q, R, info, batch, reorth);
+    LQ_CHECK_LAUNCH(c);
+    LQ_COUNT_LAUNCH(c);
+    return LQ_OK;
+}
+
 int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long batch, int m, int n, double* Q,
                          double* R, int variant) {
     if (batch == 0) return LQ_OK;
@@ -200,8 +219,13 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
                           double* Q, double* R, int* info) {
     if (batch == 0) return LQ_OK;
     if (m == 32 && n == 32) {
-        if (getenv("LINALG_B200_MGS_MINB6")) return launch_mgs32<2, 4, 2, 6>(c, st, A, batch, reorth, Q, R, info);
-        return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);
+        static const int mgs_variant = getenv("LINALG_B200_MGS_VARIANT") ? atoi(getenv("LINALG_B200_MGS_VARIANT")) : 0;  // read once
+        switch (mgs_variant) {
+            case 1: return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);        // round-1 kernel
+            case 2: return launch_mgs32_c8<7, 1, false>(c, st, A, batch, reorth, Q, R, info);
+            case 3: return launch_mgs32_c8<3, 2, true>(c, st, A, batch, reorth, Q, R, info);
+            default: return launch_mgs32_c8<7, 1, true>(c, st, A, batch, reorth, Q, R, info);
+        }
     }
     const size_t smem = small_mgs_smem_doubles(m, n, 0) * sizeof(double);
     if (smem <= (size_t)c->max_smem) {
