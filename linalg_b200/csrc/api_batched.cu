@@ -221,10 +221,11 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
     if (m == 32 && n == 32) {
         static const int mgs_variant = getenv("LINALG_B200_MGS_VARIANT") ? atoi(getenv("LINALG_B200_MGS_VARIANT")) : 0;  // read once
         switch (mgs_variant) {
-            case 1: return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);        // round-1 kernel
+            // lane = column form (round-2 experiment, profiles/ubench_r2.md): 109 M matrices/s against 135 for the default
+            case 1: return launch_mgs32_c8<7, 1, true>(c, st, A, batch, reorth, Q, R, info);
             case 2: return launch_mgs32_c8<7, 1, false>(c, st, A, batch, reorth, Q, R, info);
             case 3: return launch_mgs32_c8<3, 2, true>(c, st, A, batch, reorth, Q, R, info);
-            default: return launch_mgs32_c8<7, 1, true>(c, st, A, batch, reorth, Q, R, info);
+            default: return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);
         }
     }
     const size_t smem = small_mgs_smem_doubles(m, n, 0) * sizeof(double);
