@@ -231,6 +231,7 @@ int lq_create(int device, lq_ctx** out) {
     c->env_old_chol = getenv("LINALG_B200_OLD_CHOL") != nullptr;
     c->env_tsqr_householder = getenv("LINALG_B200_TSQR_HOUSEHOLDER") != nullptr;
     c->env_jacobi_two_sided = getenv("LINALG_B200_JACOBI_TWO_SIDED") != nullptr;
+    c->env_no_graph = getenv("LINALG_B200_NO_GRAPH") != nullptr;
     guard.c = nullptr;
     *out = c;
     return LQ_OK;
@@ -242,6 +243,9 @@ int lq_destroy(lq_ctx* h) {
     cudaSetDevice(c->device);
     lq_comm_destroy(h);
     cudaStreamSynchronize(c->stream);
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -34,6 +34,22 @@ struct Ctx : lq_ctx {
     // diagnostic kernel-selection switches: initialised from LINALG_B200_<NAME> when the context is created, changed with
     // lq_set_option (never read from the environment on a hot entry point)
     bool env_old_chol = false, env_tsqr_householder = false, env_jacobi_two_sided = false;
+    // CUDA-graph replay of the blocked QR schedule for small single matrices (launch-latency bound: 52 launches over five
+    // streams at 256^2).  Keyed by shape and the caller's device pointers; state 0 = seen once (warm-up call, runs the
+    // plain path so that every per-kernel attribute latch is set outside a capture), 1 = graph ready, -1 = not capturable.
+    struct GraphEntry {
+        int m = 0, n = 0;
+        const void* A = nullptr;
+        void* Q = nullptr;
+        void* R = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+        int state = 0;
+        unsigned long long stamp = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_clock = 0;
+    bool env_no_graph = false;
 };
 
 std::string& global_error();
