@@ -323,6 +323,38 @@ def test_least_squares_cfg3_batch(ctx):
     assert np.abs(g).max() <= 1e-10
 
 
+def test_least_squares_cfg3_full_size_batch(ctx):
+    """BASELINE cfg3 at its FULL batch (2^16 systems of 256 x 64 with 16 right-hand sides, device resident): 4096 distinct
+    systems tiled 16 x.  The 4096-system subsample is held to LAPACK at the north-star tolerance (1e-10 per system) and to
+    the normal equations A^T (A x - b) = 0; the other 15 replicas must reproduce it bit for bit (every system of the batch is
+    thereby checked); same for the MGS entry point with its dependence report all clear."""
+    uniq, reps, m, n, k = 4096, 16, 256, 64, 16
+    A = np.random.default_rng(3).standard_normal((uniq, m, n))
+    B = np.random.default_rng(4).standard_normal((uniq, m, k))
+    nsys = uniq * reps
+    dA, dB = ctx.alloc(8 * nsys * m * n), ctx.alloc(8 * nsys * m * k)
+    for r in range(reps):
+        ctx.call("lq_memcpy_h2d", dA.ptr + r * A.nbytes, A.ctypes.data, A.nbytes)
+        ctx.call("lq_memcpy_h2d", dB.ptr + r * B.nbytes, B.ctypes.data, B.nbytes)
+    ctx.sync()
+    dX, dI = ctx.alloc(8 * nsys * n * k), ctx.alloc(4 * nsys)
+    Xref = np.stack([np.linalg.lstsq(A[i], B[i], rcond=None)[0] for i in range(uniq)])
+    scale = np.max(np.abs(Xref), axis=(1, 2))
+    for name, extra in (("lq_lstsq_householder_batched_dev", ()), ("lq_lstsq_mgs_batched_dev", (dI.ptr,))):
+        ctx.call("lq_memset", dX.ptr, 0xFF, 8 * nsys * n * k)
+        ctx.call(name, dA.ptr, dB.ptr, nsys, m, n, k, dX.ptr, *extra)
+        X = ctx.download(dX, (reps, uniq, n, k))
+        assert np.max(np.max(np.abs(X[0] - Xref), axis=(1, 2)) / scale) <= REL, name
+        g = np.swapaxes(A, 1, 2) @ (A @ X[0] - B)
+        assert np.abs(g).max() <= 1e-10, name
+        for r in range(1, reps):
+            assert np.array_equal(X[r], X[0]), (name, r)
+        if extra:
+            assert not ctx.download(dI, (nsys,), dtype=np.int32).any()
+    for b in (dA, dB, dX, dI):
+        b.free()
+
+
 @pytest.mark.parametrize("m,n,k", [(50, 50, 1), (40, 12, 3), (100, 30, 7), (300, 64, 16), (64, 64, 32), (600, 200, 5), (33, 7, 40)])
 def test_least_squares_shapes(ctx, m, n, k):
     A = np.random.default_rng(m).standard_normal((m, n))
