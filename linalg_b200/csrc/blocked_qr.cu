@@ -819,13 +819,25 @@ int lq_householder_qr_dev(lq_ctx* h, const double* A, int m, int n, double* Q, d
     if ((size_t)m * n <= 4096) return hh_qr_batched_stream(c, c->stream, A, 1, m, n, Q, R, -1);
     // launch-latency-bound sizes: replay the whole multi-stream schedule as one CUDA graph (second call with the same
     // shape and buffers captures it, later calls replay it).  Measured (tools/check_graph.py): 256^2 0.78 -> 0.67 ms,
-    // 1000^2 3.51 -> 3.01, 2048^2 6.32 -> 5.63, 4096^2 15.9 -> 15.0; at 8192^2 the graph is SLOWER (65.4 vs 62.1 ms: a graph
-    // drops the stream priorities that keep the panel chain ahead of the bulk updates), hence the size cap.
-    if (c->env_no_graph || (size_t)m * n > ((size_t)1 << 24)) return blocked_householder_qr(c, A, m, n, Q, R);
+    // 1000^2 3.51 -> 2.99, 2048^2 6.32 -> 5.65, 4096^2 15.9 -> 14.7, 8192^2 62.1 -> 60.5.  The graph is instantiated with
+    // cudaGraphInstantiateFlagUseNodePriority: without the captured stream priorities (panel chain ahead of the bulk
+    // updates) the 8192^2 replay is 5 % SLOWER than the plain launches (65.4 ms).
+    if (c->env_no_graph || (size_t)m * n > ((size_t)1 << 26)) return blocked_householder_qr(c, A, m, n, Q, R);
     Ctx::GraphEntry* e = nullptr;
     for (auto& g : c->graphs)
         if (g.m == m && g.n == n && g.A == A && g.Q == Q && g.R == R) e = &g;
     if (!e) {
+        // a graph keeps its scratch allocations (4 matrix-sized buffers) alive: at most one cached graph of a large shape
+        if ((size_t)m * n > ((size_t)1 << 22)) {
+            for (size_t i = 0; i < c->graphs.size();) {
+                if ((size_t)c->graphs[i].m * c->graphs[i].n > ((size_t)1 << 22)) {
+                    if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
+                    c->graphs.erase(c->graphs.begin() + i);
+                } else {
+                    ++i;
+                }
+            }
+        }
         if (c->graphs.size() >= 8) {  // evict the least recently used entry
             size_t lru = 0;
             for (size_t i = 1; i < c->graphs.size(); ++i)
@@ -856,7 +868,7 @@ int lq_householder_qr_dev(lq_ctx* h, const double* A, int m, int n, double* Q, d
     const int rc = blocked_householder_qr(c, A, m, n, Q, R);
     const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
     cudaGraphExec_t exec = nullptr;
-    if (rc == LQ_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+    if (rc == LQ_OK && ce == cudaSuccess && graph && cudaGraphInstantiateWithFlags(&exec, graph, cudaGraphInstantiateFlagUseNodePriority) == cudaSuccess) {
         e->exec = exec;
         e->launches = c->launches - l0;
         e->state = 1;
