@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(256) jacobi_apply_kernel(const double2* __rest
     for (int j = threadIdx.x; j < n; j += blockDim.x) V[(size_t)b * n + j] = row[j];
 }
 
-// sort eigenvalues descending (rank by counting), permute the columns of V accordingly
+// sort eigenvalues descending (rank by counting), permute the columns of V accordingly.  Any number of CTAs: every CTA
+// ranks all eigenvalues itself (n^2 compares) and moves its slice of V (one CTA took 35 us at n = 128).
 __global__ void __launch_bounds__(256) eig_sort_kernel(const double* __restrict__ lam_in, const double* __restrict__ Vin, int n,
                                                        double* __restrict__ lam_out, double* __restrict__ Vout) {
     extern __shared__ int rank_of[];
@@ -455,36 +456,41 @@ __global__ void __launch_bounds__(256) eig_sort_kernel(const double* __restrict_
             rk += (lj > li) || (lj == li && j < i);
         }
         rank_of[i] = rk;
-        lam_out[rk] = li;
+        if (blockIdx.x == 0) lam_out[rk] = li;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
         const int r = e / n, cidx = e - r * n;
         Vout[(size_t)r * n + rank_of[cidx]] = Vin[e];
     }
 }
 
-// s = sqrt(max(lambda, 0)); M2 = V diag(1/s for s > tol else 0); Vt = V^T; rank = #(s > tol)
+// s = sqrt(max(lambda, 0)); M2 = V diag(1/s for s > tol else 0); Vt = V^T; rank = #(s > tol).  Any number of CTAs (one CTA
+// spent 48 us on 16 384 square roots and divisions at n = 128): the singular values are formed once per CTA in shared memory.
 __global__ void __launch_bounds__(256) svd_post_kernel(const double* __restrict__ lam, const double* __restrict__ V, int n,
                                                        double tol, double* __restrict__ s, double* __restrict__ M2,
                                                        double* __restrict__ Vt, int* __restrict__ rank) {
+    extern __shared__ double sv[];
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const double sj = sqrt(fmax(lam[j], 0.0));
-        s[j] = sj;
-        if (sj > tol) atomicAdd(&cnt, 1);
+        sv[j] = sj;
+        if (blockIdx.x == 0) {
+            s[j] = sj;
+            if (sj > tol) atomicAdd(&cnt, 1);
+        }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
         const int i = e / n, j = e - i * n;
-        const double sj = sqrt(fmax(lam[j], 0.0));
+        const double sj = sv[j];
         const double v = V[e];
         M2[e] = (sj > tol) ? v / sj : 0.0;
         Vt[(size_t)j * n + i] = v;
     }
-    if (threadIdx.x == 0) *rank = cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *rank = cnt;
 }
 
 // ------------------------------------------------------------------ small triangular helpers (single CTA)
@@ -579,12 +585,14 @@ constexpr size_t CHOL_SMEM = 128 * 129 * sizeof(double);
 // independent recurrences interleaved); lane l holds rows l + 32 u of each right-hand side in registers, R sits in
 // shared memory (odd pitch: a column walk is conflict free), 1 / R_kk is formed once.  Column-oriented back
 // substitution: x_k is broadcast from its owner lane, every lane updates its rows above k.
-__global__ void __launch_bounds__(1024) triu_inverse128_kernel(const double* __restrict__ R, int n, double* __restrict__ Rinv) {
+// The 32 warps (4 columns each) are independent: they run as 8 CTAs of 4 warps on 8 SMs (one CTA of 32 warps was bound by
+// the issue rate of a single SM: 45 us; every CTA stages its own copy of R from L2).
+__global__ void __launch_bounds__(128) triu_inverse128_kernel(const double* __restrict__ R, int n, double* __restrict__ Rinv) {
     extern __shared__ double ti_sm[];
     double (*S)[129] = reinterpret_cast<double (*)[129]>(ti_sm);
     __shared__ double dinv[128];
-    const int tid = threadIdx.x, w = tid >> 5, ln = tid & 31;
-    for (int e = tid; e < 128 * 128; e += 1024) {
+    const int tid = threadIdx.x, w = blockIdx.x * (blockDim.x >> 5) + (tid >> 5), ln = tid & 31;
+    for (int e = tid; e < 128 * 128; e += blockDim.x) {
         const int i = e >> 7, k = e & 127;
         S[i][k] = (i < n && k < n) ? R[(size_t)i * n + k] : ((i == k) ? 1.0 : 0.0);
     }
@@ -714,7 +722,7 @@ int launch_triu_inverse(Ctx* c, const double* R, int n, double* Rinv) {
             LQ_CUDA(c, cudaFuncSetAttribute(triu_inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
             configured.set(c->device);
         }
-        triu_inverse128_kernel<<<1, 1024, 128 * 129 * 8, c->stream>>>(R, n, Rinv);
+        triu_inverse128_kernel<<<8, 128, 128 * 129 * 8, c->stream>>>(R, n, Rinv);
     } else {
         triu_inverse_kernel<<<1, 256, 0, c->stream>>>(R, n, Rinv);
     }
@@ -797,6 +805,11 @@ static int gram_ld(Ctx* c, const double* A, int lda, long long m, int n, double*
 
 int gram(Ctx* c, const double* A, long long m, int n, double* G) { return gram_ld(c, A, n, m, n, G); }
 
+// CTAs for the n x n element-wise kernels behind the eigen-solver (two elements per thread at n = 128)
+static unsigned small_grid(Ctx* c, int n) {
+    return (unsigned)std::max<long long>(1, std::min<long long>(((long long)n * n + 511) / 512, (long long)c->sm_count * 2));
+}
+
 int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) {
     LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_UNSUPPORTED, "eigen-solver supports n <= 2048 (got %d)", n);
     LQ_TRY(eigh_configure(c));
@@ -828,7 +841,7 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
         LQ_CHECK_LAUNCH(c);
         eig_rayleigh_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(Aw.as<double>(), ne, Vraw.as<double>(), n, lam.as<double>());
         LQ_CHECK_LAUNCH(c);
-        eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
+        eig_sort_kernel<<<small_grid(c, n), 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
         LQ_CHECK_LAUNCH(c);
         c->launches += 4;
         return LQ_OK;
@@ -844,7 +857,7 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
     LQ_CHECK_LAUNCH(c);
     jacobi_apply_kernel<<<n, 256, sizeof(double) * (ne + 2), c->stream>>>(rot.as<double2>(), nr.as<int>(), n, ne, Vraw.as<double>());
     LQ_CHECK_LAUNCH(c);
-    eig_sort_kernel<<<1, 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
+    eig_sort_kernel<<<small_grid(c, n), 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
     LQ_CHECK_LAUNCH(c);
     c->launches += 3;
     return LQ_OK;
@@ -863,7 +876,8 @@ int svd_gram_local(Ctx* c, const double* A, long long m, int n, double tol, doub
     LQ_TRY(gram(c, A, m, n, G.as<double>()));                                  // svd.py:42
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
     LQ_TRY(eigh_jacobi(c, G.as<double>(), n, lam.as<double>(), V.as<double>())); // svd.py:46-51
-    svd_post_kernel<<<1, 256, 0, c->stream>>>(lam.as<double>(), V.as<double>(), n, tol, s, M2.as<double>(), Vt, rk.as<int>());
+    svd_post_kernel<<<small_grid(c, n), 256, sizeof(double) * n, c->stream>>>(lam.as<double>(), V.as<double>(), n, tol, s, M2.as<double>(), Vt,
+                                                                             rk.as<int>());
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
     LQ_TRY(gemm(c, false, false, m, n, n, 1.0, A, n, M2.as<double>(), n, 0.0, U, n));  // svd.py:61-64
