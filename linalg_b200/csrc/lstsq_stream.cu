@@ -51,10 +51,10 @@ bool lstsq_tile_kernel_supported(int m, int n, int nrhs) {
     return !off && n >= 1 && n <= 8 * LsTile::NCB && nrhs >= 1 && nrhs <= 8 * LsTile::NRT && m >= n;
 }
 
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool SSV = false>
 static int launch_tile(Ctx* c, cudaStream_t st, const double* A, const double* B, long long batch, int m, int n, int nrhs,
                        double* X, int* info, int info_mode) {
-    auto kern = lstsq_tile_kernel<WARPS, MINB>;
+    auto kern = lstsq_tile_kernel<WARPS, MINB, SSV>;
     const size_t smem = (size_t)WARPS * LsTile::WARP_DOUBLES * sizeof(double);
     static DeviceLatch configured;
     if (!configured.test(c->device)) {
@@ -75,6 +75,7 @@ int lstsq_tile_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const dou
     switch (variant) {
         case 1: return launch_tile<7, 1>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
         case 2: return launch_tile<8, 1>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
+        case 3: return launch_tile<4, 2, true>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);
         default: return launch_tile<4, 2>(c, st, A, B, batch, m, n, nrhs, X, info, info_mode);  // two 4-warp CTAs per SM: 17.4 ms (8 x 1: 17.8, 7 x 1: 19.9)
     }
 }
