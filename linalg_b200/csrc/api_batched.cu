@@ -145,13 +145,13 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 0:   // default (round 2): lane = column, left-looking panels, Q formation on DMMA, one 8-warp CTA per SM
             case 59: return launch_hh32_c8<8, 1, 3, true>(c, st, A, batch, Q, R);
             case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // round-1 default: reciprocal seeded from the raw rsqrt
+#ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
             case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
             case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
             case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
             case 52: return launch_hh32_c8<4, 2>(c, st, A, batch, Q, R);
             case 60: return launch_hh32_c8<8, 1, 3, false>(c, st, A, batch, Q, R);
             case 36: return launch_hh32_ll<2, 4, 3, 3, true>(c, st, A, batch, Q, R);
-#ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
             case 5: return launch_hh32<2, 4, 2, true, 4>(c, st, A, batch, Q, R);
             case 1: return launch_hh32<1, 1, 4, false, 3>(c, st, A, batch, Q, R);
             case 2: return launch_hh32<1, 2, 4, false, 2>(c, st, A, batch, Q, R);
@@ -221,10 +221,12 @@ int mgs_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long ba
     if (m == 32 && n == 32) {
         static const int mgs_variant = getenv("LINALG_B200_MGS_VARIANT") ? atoi(getenv("LINALG_B200_MGS_VARIANT")) : 0;  // read once
         switch (mgs_variant) {
+#ifdef LQ_ALL_VARIANTS
             // lane = column form (round-2 experiment, profiles/ubench_r2.md): 109 M matrices/s against 135 for the default
             case 1: return launch_mgs32_c8<7, 1, true>(c, st, A, batch, reorth, Q, R, info);
             case 2: return launch_mgs32_c8<7, 1, false>(c, st, A, batch, reorth, Q, R, info);
             case 3: return launch_mgs32_c8<3, 2, true>(c, st, A, batch, reorth, Q, R, info);
+#endif
             default: return launch_mgs32<2, 4, 2, 4>(c, st, A, batch, reorth, Q, R, info);
         }
     }
