@@ -53,7 +53,7 @@ __device__ __forceinline__ double2 lds128v(const double* p) {
 
 // PHASES: 3 = product; 1 = R phase only, 2 = Q phase only (timing diagnostics).  KEEPV: keep the broadcast reflector in
 // registers between dot product and update instead of re-reading it.
-template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false>
+template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false, bool PF2 = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     hh_qr32_c8_kernel(const double* __restrict__ A, double* __restrict__ Q, double* __restrict__ R, long long batch) {
     constexpr int N = 32;
@@ -83,14 +83,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 if (off <= last) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + off));
             }
         }
+        double nxt[PF2 ? N : 1];  // PF2: the next panel's column, loaded while this panel is being factored
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int col = 8 * p + c;
             double a[N];
-            {
+            if (!PF2 || p == 0) {
                 const double* Ag = A + matc * (N * N) + col;
 #pragma unroll
                 for (int i = 0; i < N; ++i) a[i] = ld_stream(Ag + i * N);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a[i] = nxt[i];
             }
 
             // ---- apply the reflectors of the earlier panels: a -= beta_j (v_j . a) v_j, rows j..31, all lane-local
@@ -116,6 +120,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 }
             }
 
+            if (PF2 && p < 3) {
+                // the loads of panel p + 1 fly under the 8 column steps below (their latency was ~2 k exposed cycles per panel)
+                const double* Ag = A + matc * (N * N) + col + 8;
+#pragma unroll
+                for (int i = 0; i < N; ++i) nxt[i] = ld_stream(Ag + i * N);
+            }
             // ---- factor the 8 columns of this panel
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {

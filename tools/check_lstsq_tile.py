@@ -31,6 +31,27 @@ for (b, m, n, k) in [(5, 256, 64, 16), (3, 64, 64, 16), (4, 33, 17, 3), (7, 50, 
         print(f"{name[3:22]:20s} b={b:3d} {m:4d}x{n:2d} k={k:2d}  rel err vs LAPACK {err:.2e}", flush=True)
     for x in (dA, dB, dX, dI):
         x.free()
+# randomised shapes (every m mod 32, n mod 8, nrhs): ragged last blocks, partial panels, partial right-hand-side tiles
+frng = np.random.default_rng(2026)
+for trial in range(60):
+    n = int(frng.integers(1, 65)); k = int(frng.integers(1, 17)); m = int(frng.integers(n, 700)); b = int(frng.integers(1, 40))
+    A = frng.standard_normal((b, m, n)) * 10.0 ** frng.uniform(-3, 3)
+    B = frng.standard_normal((b, m, k))
+    dA, dB, dX, dI = ctx.upload(A), ctx.upload(B), ctx.alloc(8 * b * n * k), ctx.alloc(4 * b)
+    ctx.call("lq_memset", dX.ptr, 0xFF, 8 * b * n * k)
+    ctx.call("lq_lstsq_householder_batched_info_dev", dA.ptr, dB.ptr, b, m, n, k, dX.ptr, dI.ptr)
+    X = ctx.download(dX, (b, n, k))
+    assert not ctx.download(dI, (b,), dtype=np.int32).any()
+    err = 0.0
+    for i in range(b):
+        Xo = np.linalg.lstsq(A[i], B[i], rcond=None)[0]
+        err = max(err, float(np.max(np.abs(X[i] - Xo)) / np.max(np.abs(Xo))))
+    cond = max(np.linalg.cond(A[i]) for i in range(min(b, 4)))
+    assert err < 1e-10 * max(1.0, cond / 1e3), (trial, b, m, n, k, err, cond)
+    worst = max(worst, err / max(1.0, cond / 1e3))
+    for x in (dA, dB, dX, dI):
+        x.free()
+print("60 random shapes ok; worst scaled rel err", worst, flush=True)
 # dependent columns -> info (MGS semantics), zero column -> exactly singular
 A = rng.standard_normal((4, 256, 64))
 A[1, :, 40] = A[1, :, 3] * 2.0
