@@ -145,9 +145,9 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 0:   // default (round 2): lane = column, left-looking panels, Q formation on DMMA, one 8-warp CTA per SM
             case 59: return launch_hh32_c8<8, 1, 3, true>(c, st, A, batch, Q, R);
             case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // round-1 default: reciprocal seeded from the raw rsqrt
+#ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
             case 80: return launch_hh32_c8<8, 1, 3, true, false, true>(c, st, A, batch, Q, R);   // next panel prefetched into registers
             case 81: return launch_hh32_c8<8, 1, 3, false, false, true>(c, st, A, batch, Q, R);
-#ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
             case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
             case 13: return launch_hh32_pipe<2, 4, 2>(c, st, A, batch, Q, R);
             case 21: return launch_hh32_dmma<4, 2>(c, st, A, batch, Q, R);
