@@ -383,7 +383,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
                   int nrhs_pad, Factored* keep) {
     const int nblocks = (nfac + NB_OUT - 1) / NB_OUT;
     cudaStream_t s_main = c->stream, s_side = c->lane[0], s_aux = c->lane[1], s_merge = c->lane[2], s_side2 = c->lane[3];
-    const bool lookahead = (getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr) && nblocks > 1;
+    const bool lookahead = (!LQ_ENV_ONCE("LINALG_B200_NO_LOOKAHEAD")) && nblocks > 1;
     // Gram scratch of the T merge: one buffer per stream that may run a merge (main: blocks without panel-wise look-ahead,
     // e.g. the last one; merge stream: all the others) -- the two streams are not ordered against each other
     DevBuf Tloc, G, Gmerge, W, W2, Ws, W2s, W2s2;
@@ -393,7 +393,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     LQ_TRY(W.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     LQ_TRY(W2.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
     DevBuf Wa, W2a;  // scratch of the aux stream (panel-wise application to the next outer block)
-    const bool pw_lookahead = getenv("LINALG_B200_NO_PANELWISE") == nullptr;
+    const bool pw_lookahead = !LQ_ENV_ONCE("LINALG_B200_NO_PANELWISE");
     if (lookahead) {
         LQ_TRY(Ws.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
         LQ_TRY(W2s.alloc(c, sizeof(double) * NB_OUT * (size_t)wcols));
@@ -414,7 +414,7 @@ int factor_padded(Ctx* c, double* A, int lda, int m, int npad, int nfac, double*
     EventPool pool;
     // diagnostics (LINALG_B200_TRACE_BLOCKS=1): per outer block, when the panel chain, the next-block update and the
     // side stream's trailing update finished (ms since the start of the factorisation), printed to stderr
-    const bool trace_blocks = lookahead && getenv("LINALG_B200_TRACE_BLOCKS") != nullptr;
+    const bool trace_blocks = lookahead && LQ_ENV_ONCE("LINALG_B200_TRACE_BLOCKS");
     pool.timing = trace_blocks;
     struct BlockTrace { cudaEvent_t panels = nullptr, chain = nullptr, next = nullptr, rest = nullptr; };
     std::vector<BlockTrace> btrace(trace_blocks ? nblocks : 0);
@@ -717,12 +717,12 @@ int blocked_householder_qr(Ctx* c, const double* A, int m, int n, double* Q, dou
     set_identity_kernel<<<grid_for(c, (long long)m * ldq), 256, 0, c->stream>>>(Qp, ldq, m, ldq);
     LQ_CHECK_LAUNCH(c);
     LQ_COUNT_LAUNCH(c);
-    const bool skip_q = getenv("LINALG_B200_DEBUG_SKIP_Q") != nullptr;  // timing experiments only (Q = I)
+    const bool skip_q = LQ_ENV_ONCE("LINALG_B200_DEBUG_SKIP_Q");  // timing experiments only (Q = I)
     // A block reflector transforms every COLUMN of Q independently, so the columns are split into two contiguous
     // ranges that run the whole chain of applications on two streams with no synchronisation in between: the launch
     // gaps, split-K reductions and partial last waves of one range are filled by the other.  The split balances the
     // flops (block b touches the columns >= 128 b only): 3 s^2 - s^3 = 1  ->  s = 0.65.
-    const bool two_ranges = ldq >= 2048 && ws_fits && getenv("LINALG_B200_NO_LOOKAHEAD") == nullptr;
+    const bool two_ranges = ldq >= 2048 && ws_fits && !LQ_ENV_ONCE("LINALG_B200_NO_LOOKAHEAD");
     const int split = two_ranges ? (int)(0.65 * ldq) / NB_OUT * NB_OUT : 0;
     cudaStream_t s_main = c->stream, s_side = c->lane[0];
     EventPool qpool;

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -54,6 +55,9 @@ void set_error(Ctx* c, const char* fmt, ...);
         int _rc = (expr);                                                                   \
         if (_rc != 0) return _rc;                                                           \
     } while (0)
+
+// Diagnostic environment switches are read ONCE per call site (never on a hot path: a blocked QR issues thousands of GEMMs)
+#define LQ_ENV_ONCE(name) ([]() -> bool { static const bool v = ::getenv(name) != nullptr; return v; }())
 
 // Per-device "this kernel's attributes are set" latch.  Two host threads (two contexts) may race to the first launch:
 // both then set the (idempotent) attribute and both publish the flag -- no torn state, no lock on the hot path.

@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_rank_kernel(const RankAr
 // returns LQ_ERR_UNSUPPORTED when the shape is not a rank-K product this kernel takes
 int gemm_rank(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
               double* C, int ldc) {
-    if (getenv("LINALG_B200_NO_RANK_GEMM")) return LQ_ERR_UNSUPPORTED;
+    if (LQ_ENV_ONCE("LINALG_B200_NO_RANK_GEMM")) return LQ_ERR_UNSUPPORTED;
     if (K > RK_KT_MAX * BK || K % BK != 0 || K < BK || (N % 2) != 0 || M < 2 * BM) return LQ_ERR_UNSUPPORTED;
     const long long tm = (M + BM - 1) / BM;
     const int tn = (N + BN - 1) / BN;
@@ -792,7 +792,7 @@ int gemm_rank(Ctx* c, long long M, int N, int K, double alpha, const double* A, 
     if (!astat && tm < 4) return LQ_ERR_UNSUPPORTED;
     // measured on B200: the B-stationary walk wins on tall-skinny products (30.2 vs 27.8 TFLOP/s at 2^20 x 128 x 128),
     // the A-stationary walk does not beat the generic kernel on square block updates (23.6 vs 25.0) -> opt-in only
-    if (astat && !getenv("LINALG_B200_RANK_ASTAT")) return LQ_ERR_UNSUPPORTED;
+    if (astat && !LQ_ENV_ONCE("LINALG_B200_RANK_ASTAT")) return LQ_ERR_UNSUPPORTED;
     static DeviceLatch configured;
     if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(gemm_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RK_SMEM_ASTAT));
@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_upd_kernel(const UpdArgs
 // C (+)= alpha * A * B for row-major A (M x K, lda), B (K x N, ldb), K a small multiple of 16; LQ_ERR_UNSUPPORTED otherwise
 int gemm_update(Ctx* c, long long M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C,
                 int ldc, bool overwrite) {
-    if (getenv("LINALG_B200_NO_UPD_GEMM")) return LQ_ERR_UNSUPPORTED;
+    if (LQ_ENV_ONCE("LINALG_B200_NO_UPD_GEMM")) return LQ_ERR_UNSUPPORTED;
     if (K % BK != 0 || K < BK || K > 512 || (N % 2) != 0 || (ldc % 2) != 0 || !aligned16(C) || M < BM || N < UBN)
         return LQ_ERR_UNSUPPORTED;
     const long long tm = (M + BM - 1) / BM;
@@ -1012,7 +1012,7 @@ int gemm(Ctx* c, bool ta, bool tb, long long M, int N, int K, double alpha, cons
     bool fast = Kmain >= BK && aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0) && (M * (long long)N >= 32 * 32);
     if (ta) fast = fast && (M % 2 == 0);   // M-major rows copied in whole 16-byte units
     if (!tb) fast = fast && (N % 2 == 0);
-    if (getenv("LINALG_B200_NO_FAST_GEMM")) fast = false;
+    if (LQ_ENV_ONCE("LINALG_B200_NO_FAST_GEMM")) fast = false;
     if (!fast) {
         if (ta && tb) return launch_generic<true, true>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
         if (ta) return launch_generic<true, false>(c, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -1055,13 +1055,13 @@ int vtc_finish(Ctx* c, const double* partials, int splits, long long stride, int
 int gemm_vtc_apply_t(Ctx* c, int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc, const double* T,
                      int ldt, bool trans_t, double* W2) {
     if (kb <= 0 || nc <= 0) return LQ_OK;
-    if (getenv("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, nc, mk, V, ldv, Cm, ldc)) {
+    if (LQ_ENV_ONCE("LINALG_B200_VTC_CLUSTER") && vtc_cluster_supported(kb, nc, mk, V, ldv, Cm, ldc)) {
         const int rc = vtc_cluster(c, trans_t ? 1 : 2, kb, nc, mk, V, ldv, Cm, ldc, T, ldt, W2);
         if (rc != LQ_ERR_UNSUPPORTED) return rc;
     }
     const int Kmain = mk - mk % BK;
     const bool fast = kb <= 128 && Kmain >= BK && Kmain == mk && aligned16(V) && aligned16(Cm) && (ldv % 2 == 0) &&
-                      (ldc % 2 == 0) && (kb % 4 == 0) && (nc % 2 == 0) && !getenv("LINALG_B200_NO_FAST_GEMM");
+                      (ldc % 2 == 0) && (kb % 4 == 0) && (nc % 2 == 0) && !LQ_ENV_ONCE("LINALG_B200_NO_FAST_GEMM");
     if (!fast) {
         DevBuf W;
         LQ_TRY(W.alloc(c, sizeof(double) * (size_t)kb * nc));

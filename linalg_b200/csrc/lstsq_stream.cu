@@ -7,7 +7,7 @@
 namespace lq {
 
 bool lstsq_stream_kernel_supported(int m, int n, int nrhs) {
-    if (getenv("LINALG_B200_NO_STREAM_LSTSQ")) return false;
+    if (LQ_ENV_ONCE("LINALG_B200_NO_STREAM_LSTSQ")) return false;
     return n >= 1 && n <= 64 && nrhs >= 1 && nrhs <= 32 && m >= n;
 }
 
@@ -47,7 +47,7 @@ int lstsq_stream_kernel_launch(Ctx* c, cudaStream_t st, const double* A, const d
 
 // ---- round 2: one warp per system, block reflectors on DMMA (lstsq_tile.cuh); n <= 64, nrhs <= 16
 bool lstsq_tile_kernel_supported(int m, int n, int nrhs) {
-    static const bool off = getenv("LINALG_B200_NO_TILE_LSTSQ") != nullptr;
+    static const bool off = LQ_ENV_ONCE("LINALG_B200_NO_TILE_LSTSQ");
     return !off && n >= 1 && n <= 8 * LsTile::NCB && nrhs >= 1 && nrhs <= 8 * LsTile::NRT && m >= n;
 }
 

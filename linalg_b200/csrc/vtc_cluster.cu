@@ -214,7 +214,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 bool vtc_cluster_supported(int kb, int nc, int mk, const double* V, int ldv, const double* Cm, int ldc) {
-    if (getenv("LINALG_B200_NO_VTC_CLUSTER")) return false;
+    if (LQ_ENV_ONCE("LINALG_B200_NO_VTC_CLUSTER")) return false;
     return kb >= 2 && kb <= 128 && (kb % 2 == 0) && nc >= 2 && (nc % 2 == 0) && mk >= BK && (mk % BK == 0) &&
            aligned16(V) && aligned16(Cm) && (ldv % 2 == 0) && (ldc % 2 == 0);
 }
