@@ -289,7 +289,7 @@ int launch_cluster(Ctx* c, Kern kern, int cs, int threads, Args... args) {
     return LQ_OK;
 }
 
-// version: 0 = default choice, 1 = barrier.cluster kernel (panel.cuh), 2 = st.async kernel (panel2.cuh), 16 rows per lane,
+// version: 0 = default choice (panels of up to 256 rows: the one-CTA SOLO kernel), 1 = barrier.cluster kernel (panel.cuh), 2 = st.async kernel (panel2.cuh), 16 rows per lane,
 // 3 = st.async kernel with 8 rows per lane (256 rows per CTA), 4 = st.async kernels for every height (256 rows per CTA up to
 // 4096 rows, 512 above)
 int panel_factor_v(Ctx* c, double* A, int lda, double* V, int ldv, double* T, int ldt, int mp, int nb, int version) {
@@ -309,6 +309,13 @@ int panel_factor_v(Ctx* c, double* A, int lda, double* V, int ldv, double* T, in
         // default: the 256-rows-per-CTA kernel whenever the panel fits a cluster of it (half the FP64 work per SM and
         // column); taller panels run next to the side stream's big GEMMs, where the barrier.cluster kernel measured
         // better in situ (tools/blocked_trace.py), although the 512-row st.async kernel wins stand-alone
+        if (version == 0 && mp <= Panel2Cfg<8>::ROWS_PER_CTA && !LQ_ENV_ONCE("LINALG_B200_NO_SOLO_PANEL")) {
+            // one CTA, no cluster exchange: ~17 us instead of 48 us per panel of up to 256 rows
+            panel2_cluster_kernel<8, false, true><<<1, P2_THREADS, 0, c->stream>>>(A, lda, V, ldv, T, ldt, mp, (long long*)nullptr);
+            LQ_CHECK_LAUNCH(c);
+            LQ_COUNT_LAUNCH(c);
+            return LQ_OK;
+        }
         if (version != 2 && mp <= maxcs * Panel2Cfg<8>::ROWS_PER_CTA) {
             int cs = 1;
             while (cs * Panel2Cfg<8>::ROWS_PER_CTA < mp) cs *= 2;

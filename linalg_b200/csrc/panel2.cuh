@@ -59,6 +59,7 @@ struct __align__(16) Panel2Smem {
     double rdiag[32];                                   // R[j][j]
     double rn[32];                                      // 1 / ||v_c||  (0 if skipped)
     double nv[32];                                      // ||v_c||      (0 if skipped)
+    double gall[32][33];                                // SOLO kernel: g of every column (T is built after the column loop)
     uint64_t bar[2];
 };
 
@@ -69,7 +70,11 @@ struct __align__(16) Panel2Smem {
             trace[((t_warp ? 1 : 0) * 32 + j) * 8 + (slot)] = clock64();                \
     } while (0)
 
-template <int RPT, bool TRACE>
+// SOLO (round 2): the panel fits ONE CTA (mp <= 32 RPT rows).  The whole st.async / mbarrier exchange disappears (it cost ~1.5 us
+// per column even for a 33-row panel: 48 us per panel whatever its height): after the one block barrier of the column every warp
+// sums the eight per-warp partials itself.  The T recurrence, which the cluster kernel hides in the shadow of the exchange, is
+// done once after the column loop from the saved g vectors.  Plain (non-cluster) launch.
+template <int RPT, bool TRACE, bool SOLO = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
     panel2_cluster_kernel(double* __restrict__ A, int lda, double* __restrict__ V, int ldv, double* __restrict__ T, int ldt,
                           int mp, long long* __restrict__ trace) {
@@ -79,8 +84,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int p = lane >> 3, lc = lane & 7;
-    const int q = (int)cluster_ctarank();
-    const int CS = (int)cluster_nctarank();
+    const int q = SOLO ? 0 : (int)cluster_ctarank();
+    const int CS = SOLO ? 1 : (int)cluster_nctarank();
     const int rowbase = q * Cfg::ROWS_PER_CTA + w * Cfg::ROWS_PER_WARP;
     const bool top_warp = (q == 0) && (w == 0);              // holds rows 0 .. 4*RPT-1, i.e. the whole top block
     const bool t_warp = (q == CS - 1) && (w == P2_WARPS - 1);  // maintains the T factor
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         mbar_fence_init();
     }
     __syncthreads();
-    cluster_sync_all();  // every CTA's barriers are initialised before the first remote store
+    if (!SOLO) cluster_sync_all();  // every CTA's barriers are initialised before the first remote store
 
     const uint32_t expect_bytes = (uint32_t)(CS * 32 * sizeof(double) + 32 * sizeof(double));
     // my two push targets
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         const int par = j & 1;
 
         P2_STAMP(0);
-        if (threadIdx.x == 0) mbar_expect_tx(&sm.bar[par], expect_bytes);  // arm this column's phase
+        if (!SOLO && threadIdx.x == 0) mbar_expect_tx(&sm.bar[par], expect_bytes);  // arm this column's phase
 
         // ---- owner lanes publish their part of column j
         if (lc == lo) {
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         P2_STAMP(2);
 
         // ---- every warp forms the CTA sum (lane = column) and pushes it to its two target CTAs
-        {
+        if (!SOLO) {
             double s0 = sm.part[par][0][lane] + sm.part[par][1][lane];
             double s1 = sm.part[par][2][lane] + sm.part[par][3][lane];
             double s2 = sm.part[par][4][lane] + sm.part[par][5][lane];
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         P2_STAMP(3);
         // ---- T column of the PREVIOUS reflector, in the shadow of the exchange
         //      T_u[0:jj, jj] = -beta_jj * T_u[0:jj, 0:jj] * g[0:jj],  T_u[jj][jj] = beta_jj
-        if (j > 0 && t_warp) {
+        if (!SOLO && j > 0 && t_warp) {
             const int jj = j - 1;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
@@ -222,12 +227,20 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
 
         // ---- wait for the column's data from every CTA
         P2_STAMP(4);
-        mbar_wait(&sm.bar[par], (uint32_t)((j >> 1) & 1));
+        if (!SOLO) mbar_wait(&sm.bar[par], (uint32_t)((j >> 1) & 1));
         P2_STAMP(5);
 
         // totals: lane c holds column c.  Always 16 slots (the unused ones stay zero): no loop, no branches
-        double tot;
-        {
+        double tot, prow, x0;
+        if (SOLO) {
+            const double s0 = sm.part[par][0][lane] + sm.part[par][1][lane];
+            const double s1 = sm.part[par][2][lane] + sm.part[par][3][lane];
+            const double s2 = sm.part[par][4][lane] + sm.part[par][5][lane];
+            const double s3 = sm.part[par][6][lane] + sm.part[par][7][lane];
+            tot = (s0 + s1) + (s2 + s3);
+            prow = sm.ppart[par][lane];
+            x0 = sm.ppart[par][j];
+        } else {
             double tt[P2_MAXCS];
 #pragma unroll
             for (int t = 0; t < P2_MAXCS; ++t) tt[t] = sm.recv[par][t][lane];
@@ -236,9 +249,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
 #pragma unroll
                 for (int t = 0; t < o; ++t) tt[t] += tt[t + o];
             tot = tt[0];
+            prow = sm.precv[par][lane];
+            x0 = sm.precv[par][j];                             // pivot (broadcast load)
         }
-        const double prow = sm.precv[par][lane];
-        const double x0 = sm.precv[par][j];                   // pivot (broadcast load)
         const double ss = __shfl_sync(0xffffffffu, tot, j);   // sum_{r>=j} x_r^2
         // y = 1/||x||;  beta = 2 / v^T v = 1 / (||x|| (||x|| + |x0|)) = y^2 / (1 + |x0| y).  The reciprocal's seed comes
         // from the unrefined y, so its MUFU runs beside the Newton steps of y instead of behind them.
@@ -297,15 +310,38 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
             sm.v0[j] = v0;
             sm.rdiag[j] = skip ? x0 : -alpha;
         }
-        if (t_warp) {
+        if (SOLO) {
+            if (w == 0) sm.gall[j][lane] = gl;
+        } else if (t_warp) {
             __syncwarp();
             sm.gsave[lane] = gl;
             beta_prev = beta;
             __syncwarp();
         }
     }
+    if (SOLO) {
+        // T_u[0:jj, jj] = -beta_jj T_u[0:jj, 0:jj] g_jj[0:jj], T_u[jj][jj] = beta_jj: one warp, lane = row of T_u
+        __syncthreads();
+        if (w == 0) {
+            for (int jj = 0; jj < NB; ++jj) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int k = 0; k + 3 < jj; k += 4) {
+                    a0 = fma(sm.Tt[k][lane], sm.gall[jj][k], a0);
+                    a1 = fma(sm.Tt[k + 1][lane], sm.gall[jj][k + 1], a1);
+                    a2 = fma(sm.Tt[k + 2][lane], sm.gall[jj][k + 2], a2);
+                    a3 = fma(sm.Tt[k + 3][lane], sm.gall[jj][k + 3], a3);
+                }
+                for (int k = jj & ~3; k < jj; ++k) a0 = fma(sm.Tt[k][lane], sm.gall[jj][k], a0);
+                const double bj = sm.beta[jj];
+                __syncwarp();
+                if (lane < jj) sm.Tt[jj][lane] = -bj * ((a0 + a1) + (a2 + a3));
+                if (lane == jj) sm.Tt[jj][lane] = bj;
+                __syncwarp();
+            }
+        }
+    }
     // T column of the last reflector
-    if (t_warp) {
+    if (!SOLO && t_warp) {
         const int jj = NB - 1;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -362,7 +398,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
             T[(long long)i * ldt + k] = val;
         }
     }
-    cluster_sync_all();  // nobody exits while a peer may still target its shared memory
+    if (!SOLO) cluster_sync_all();  // nobody exits while a peer may still target its shared memory
 }
 
 }  // namespace lq

@@ -23,13 +23,14 @@ def run(A, version, reps=0):
     for b in (dA, dV, dT): b.free()
     return np.triu(R), V, T, t
 def rel(a, b): return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
-for m in (8192, 5000, 4096, 2048, 1000, 512, 300, 64, 33):
+for m in (8192, 5000, 4096, 2048, 1000, 512, 300, 256, 200, 64, 33, 32):
     A = np.random.default_rng(m).standard_normal((m, 32))
-    if m == 300: A[:, 7] = 0.0; A[:, 20] = A[:, 3]   # a skipped reflector and a dependent column
+    if m in (300, 200): A[:, 7] = 0.0; A[:, 20] = A[:, 3]   # a skipped reflector and a dependent column
     Qn, Rn = np.linalg.qr(A)
     ref = run(A, 1, 20)
     line = f"m={m:5d} v1 {ref[3]:7.1f} us"
-    for ver in (2, 3):
+    for ver in (2, 3, 0):
+        if ver == 0 and m > 256: continue   # version 0 = default: the one-CTA SOLO kernel up to 256 rows
         if ver == 2 and m > 16 * 512: continue
         if ver == 3 and m > 16 * 256: continue
         got = run(A, ver, 20)
