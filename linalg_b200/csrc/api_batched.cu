@@ -88,10 +88,10 @@ static int launch_hh32_ll(Ctx* c, cudaStream_t st, const double* A, long long ba
 }
 
 // lane = column, four matrices per warp, left-looking panels + DMMA Q phase
-template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false, bool PF2 = false>
+template <int WARPS, int MINB, int PHASES = 3, bool KEEPV = false, bool PF = false, bool PF2 = false, typename LAY = Col8>
 static int launch_hh32_c8(Ctx* c, cudaStream_t st, const double* A, long long batch, double* Q, double* R) {
-    auto kern = hh_qr32_c8_kernel<WARPS, MINB, PHASES, KEEPV, PF, PF2>;
-    const size_t smem = (size_t)WARPS * Col8::WARP_DOUBLES * sizeof(double);
+    auto kern = hh_qr32_c8_kernel<WARPS, MINB, PHASES, KEEPV, PF, PF2, LAY>;
+    const size_t smem = (size_t)WARPS * LAY::WARP_DOUBLES * sizeof(double);
     static DeviceLatch configured;
     if (!configured.test(c->device)) {
         LQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -146,6 +146,7 @@ int hh_qr_batched_stream(Ctx* c, cudaStream_t st, const double* A, long long bat
             case 59: return launch_hh32_c8<8, 1, 3, true>(c, st, A, batch, Q, R);
             case 14: return launch_hh32<2, 4, 2, true, 4, -1>(c, st, A, batch, Q, R);  // round-1 default: reciprocal seeded from the raw rsqrt
 #ifdef LQ_ALL_VARIANTS  // design-space variants measured in profiles/ (build with LINALG_B200_ALL_VARIANTS=1; tools/sweep_hh32.py)
+            case 82: return launch_hh32_c8<8, 1, 3, true, false, false, Col8P>(c, st, A, batch, Q, R);  // padded reflector storage
             case 80: return launch_hh32_c8<8, 1, 3, true, false, true>(c, st, A, batch, Q, R);   // next panel prefetched into registers
             case 81: return launch_hh32_c8<8, 1, 3, false, false, true>(c, st, A, batch, Q, R);
             case 6: return launch_hh32<2, 4, 2, true, 4, 2>(c, st, A, batch, Q, R);   // 2 Newton steps, reciprocal behind the norm
