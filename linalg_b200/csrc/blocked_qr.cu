@@ -811,6 +811,11 @@ int lq_debug_panel_trace(lq_ctx* h, double* A, int lda, double* V, int ldv, doub
     LQ_CUDA(c, cudaSetDevice(c->device));
     const int maxcs = detect_max_cluster(c);
     LQ_REQUIRE(c, mp <= maxcs * Panel2Cfg<8>::ROWS_PER_CTA, LQ_ERR_SHAPE, "panel too tall for the traced kernel");
+    if (mp <= Panel2Cfg<8>::ROWS_PER_CTA && !LQ_ENV_ONCE("LINALG_B200_NO_SOLO_PANEL")) {  // the one-CTA kernel's stamps
+        panel2_cluster_kernel<8, true, true><<<1, P2_THREADS, 0, c->stream>>>(A, lda, V, ldv, T, ldt, mp, trace);
+        LQ_CHECK_LAUNCH(c);
+        return LQ_OK;
+    }
     cudaFuncSetAttribute(panel2_cluster_kernel<8, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     int cs = 1;
     while (cs * Panel2Cfg<8>::ROWS_PER_CTA < mp) cs *= 2;
