@@ -432,6 +432,41 @@ def main():
         ctx2.close()
     except Exception as exc:  # diagnostics only
         e2e["copy_ceiling"] = {"error": repr(exc)}
+    # the in-process multi-GPU form of the same call (`devices=`): rank 0 alone fans a 2^18-matrix batch
+    # over every GPU of the launch from ONE process (one host thread + context per GPU, no communication) while the other
+    # ranks wait; the result is compared with the single-GPU call bit for bit
+    if info.world > 1 and not args.no_extras:
+        try:
+            from linalg_b200 import _native as _nat
+
+            ndev = min(info.world, _nat.device_count())
+            d.barrier()
+            if info.rank == 0 and ndev > 1:
+                nb = min(1 << 18, e2e_batch)
+                devs = [ctx.device] + [k for k in range(ndev) if k != ctx.device]
+                Q1, R1 = lb.householder_qr_batched(hA[:nb], out=(hQ[:nb], hR[:nb]), ctx=ctx)
+                Qd, Rd = lb.pinned_empty((nb, N32, N32)), lb.pinned_empty((nb, N32, N32))
+                lb.householder_qr_batched(hA[:nb], out=(Qd, Rd), devices=devs)          # warm-up: contexts, staging lanes
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    lb.householder_qr_batched(hA[:nb], out=(Qd, Rd), devices=devs)
+                dt = (time.perf_counter() - t0) / 3
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    lb.householder_qr_batched(hA[:nb], out=(hQ[:nb], hR[:nb]), ctx=ctx)
+                dt1 = (time.perf_counter() - t0) / 3
+                same = bool(np.array_equal(Qd, Q1) and np.array_equal(Rd, R1))
+                _require(same, "devices= result bitwise equal to the one-GPU call", same)
+                e2e["devices_kwarg"] = {"devices": devs, "batch": nb, "matrices_per_s": nb / dt, "one_gpu_matrices_per_s": nb / dt1,
+                                        "bitwise_equal_to_one_gpu": same,
+                                        "api": "householder_qr_batched(A, devices=[...]) from ONE process, the other ranks idle"}
+                del Qd, Rd
+            d.barrier()
+        except ParityError:
+            raise
+        except Exception as exc:  # diagnostics only
+            e2e["devices_kwarg"] = {"error": repr(exc)}
+            d.barrier()
     del hA, hQ, hR
     dA.free(); dQ.free(); dR.free()
 
