@@ -68,7 +68,11 @@ int lq_set_option(lq_ctx* ctx, const char* name, int value);
 int lq_householder_qr_batched_dev(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, double* Q, double* R,
                                   int variant);
 int lq_householder_qr_batched(lq_ctx* ctx, const double* A, int64_t batch, int m, int n, double* Q, double* R);
-/* single (possibly large) matrix: blocked compact-WY Householder */
+/* single (possibly large) matrix: blocked compact-WY Householder.
+ * lq_householder_qr_dev replays its multi-stream launch schedule as a CUDA graph from the third call with the same shape AND the
+ * same three device pointers (first call: plain launches, second: capture; up to 8 shapes are cached per context, one of them
+ * larger than 2048^2).  The graph holds pointers, not data: the buffers' contents may change between calls.  Results are bit
+ * for bit those of the plain launches; LINALG_B200_NO_GRAPH=1 disables the replay. */
 int lq_householder_qr_dev(lq_ctx* ctx, const double* A, int m, int n, double* Q, double* R);
 int lq_householder_qr(lq_ctx* ctx, const double* A, int m, int n, double* Q, double* R);
 
