@@ -52,7 +52,9 @@ int syrk_tn(Ctx* c, const double* A, int lda, long long m, int n, double* G, int
 
 // ---- tallskinny.cu
 int gram(Ctx* c, const double* A, long long m, int n, double* G);  // G = A^T A
-int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V);
+// psd: the caller guarantees a positive semi-definite G (a Gram matrix): a well-conditioned one then gets its eigenvectors as
+// the normalised converged columns b_i = lambda_i v_i instead of replaying the rotation log
+int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V, bool psd = false);
 int svd_gram_local(Ctx* c, const double* A, long long m, int n, double tol, double* U, double* s, double* Vt,
                    int* rank_host, bool sharded);
 int tsqr_local(Ctx* c, const double* A, long long m, int n, double* Q, double* R, bool sharded);

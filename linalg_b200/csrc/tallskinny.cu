@@ -241,7 +241,8 @@ __device__ __forceinline__ void jacobi1s_rotate(double (&ap)[2 * NUMAX], double 
 template <int NU_T>  // NU_T = 8: the n = 128 specialisation (no row guards); 0: ne / 16 at run time
 __global__ void __launch_bounds__(512) jacobi1s_kernel(const double* __restrict__ G, int n, int ne, double2* __restrict__ rotlog,
                                                        int max_sweeps, double rel_tol, int* __restrict__ nsteps_out,
-                                                       double* __restrict__ Bout, unsigned short* __restrict__ pairtab) {
+                                                       double* __restrict__ Bout, unsigned short* __restrict__ pairtab,
+                                                       double* __restrict__ colnorm, int allow_direct) {
     constexpr int NUMAX = 8;
     extern __shared__ __align__(16) double Bm[];  // ne x ne, column-major
     __shared__ int s_rot;
@@ -347,6 +348,39 @@ __global__ void __launch_bounds__(512) jacobi1s_kernel(const double* __restrict_
     }
     if (tid == 0) *nsteps_out = step_base;
     for (int e = tid; e < ne * ne; e += nt) Bout[e] = Bm[e];
+    // The converged columns are b_i = G v_i = lambda_i v_i: for a well-conditioned PSD matrix the eigenvectors are simply the
+    // normalised columns (error ~ eps lambda_max / lambda_i), and the replay of the rotation log (0.22 ms at n = 128) can be
+    // skipped.  nsteps_out[1] = 1 tells the two follow-up kernels to take that route (lambda_min > 1e-2 lambda_max: vectors to ~1e-14).
+    __shared__ double s_cn[128];
+    for (int col = tid >> 3; col < ne; col += nt >> 3) {
+        double a[2 * NUMAX];
+        load_col(col, a);
+        double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < NUMAX; ++u)
+            if (u < NU) n0 = fma(a[2 * u], a[2 * u], n0), n1 = fma(a[2 * u + 1], a[2 * u + 1], n1);
+        double nn = n0 + n1;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        if (r8 == 0) s_cn[col] = sqrt(nn);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) colnorm[i] = s_cn[i];
+    if (tid == 0) {
+        double mn = 1e300, mx = 0.0;
+        for (int i = 0; i < n; ++i) mn = fmin(mn, s_cn[i]), mx = fmax(mx, s_cn[i]);
+        nsteps_out[1] = (allow_direct && mx > 0.0 && mn > 1e-2 * mx) ? 1 : 0;
+    }
+}
+
+// V[:, i] = b_i / ||b_i|| when the Jacobi kernel found the matrix well conditioned (see there); V row-major n x n
+__global__ void __launch_bounds__(256) eigvec_from_b_kernel(const double* __restrict__ B, int ne, const double* __restrict__ colnorm,
+                                                            const int* __restrict__ flags, int n, double* __restrict__ V) {
+    if (flags[1] == 0) return;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int j = e / n, i = e - j * n;  // V[j][i] = B[row j of column i]
+        V[e] = B[(size_t)i * ne + j] / colnorm[i];
+    }
 }
 
 // V = J_1 J_2 ... for the one-sided kernel's log: one WARP per row of V (the row lives in warp-private shared memory,
@@ -357,7 +391,7 @@ __global__ void __launch_bounds__(128) jacobi1s_apply_kernel(const double2* __re
     __shared__ double rows[4][128];
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + wid;
-    if (b >= n) return;
+    if (b >= n || nsteps[1] != 0) return;  // (well-conditioned matrix: the eigenvectors come straight from B)
     double* row = rows[wid];
     for (int j = ln; j < ne; j += 32) row[j] = (j == b) ? 1.0 : 0.0;
     __syncwarp();
@@ -810,7 +844,7 @@ static unsigned small_grid(Ctx* c, int n) {
     return (unsigned)std::max<long long>(1, std::min<long long>(((long long)n * n + 511) / 512, (long long)c->sm_count * 2));
 }
 
-int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) {
+int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V, bool psd) {
     LQ_REQUIRE(c, n >= 1 && n <= 2048, LQ_ERR_UNSUPPORTED, "eigen-solver supports n <= 2048 (got %d)", n);
     LQ_TRY(eigh_configure(c));
     const int max_sweeps = 40;
@@ -829,21 +863,25 @@ int eigh_jacobi(Ctx* c, const double* G, int n, double* lambda_desc, double* V) 
         LQ_TRY(Aw.alloc(c, sizeof(double) * (size_t)ne * ne));
         LQ_TRY(rot.alloc(c, sizeof(double2) * (size_t)(max_sweeps + 1) * jacobi1s_steps_per_sweep(ne) * 64));
         LQ_TRY(ptab.alloc(c, sizeof(unsigned short) * (size_t)jacobi1s_steps_per_sweep(ne) * 64));
+        const int direct = (psd && !LQ_ENV_ONCE("LINALG_B200_JACOBI_ALWAYS_REPLAY")) ? 1 : 0;
         if (ne == 128)
             jacobi1s_kernel<8><<<1, 512, sizeof(double) * (size_t)ne * ne, c->stream>>>(G, n, ne, rot.as<double2>(), max_sweeps, rel_tol,
-                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>());
+                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>(), lam.as<double>(), direct);
         else
             jacobi1s_kernel<0><<<1, 512, sizeof(double) * (size_t)ne * ne, c->stream>>>(G, n, ne, rot.as<double2>(), max_sweeps, rel_tol,
-                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>());
+                                                                                       nr.as<int>(), Aw.as<double>(), ptab.as<unsigned short>(), lam.as<double>(), direct);
         LQ_CHECK_LAUNCH(c);
         jacobi1s_apply_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(rot.as<double2>(), nr.as<int>(), ptab.as<unsigned short>(), n, ne,
                                                                    Vraw.as<double>());
+        LQ_CHECK_LAUNCH(c);
+        if (direct)
+            eigvec_from_b_kernel<<<small_grid(c, n), 256, 0, c->stream>>>(Aw.as<double>(), ne, lam.as<double>(), nr.as<int>(), n, Vraw.as<double>());
         LQ_CHECK_LAUNCH(c);
         eig_rayleigh_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(Aw.as<double>(), ne, Vraw.as<double>(), n, lam.as<double>());
         LQ_CHECK_LAUNCH(c);
         eig_sort_kernel<<<small_grid(c, n), 256, sizeof(int) * n, c->stream>>>(lam.as<double>(), Vraw.as<double>(), n, lambda_desc, V);
         LQ_CHECK_LAUNCH(c);
-        c->launches += 4;
+        c->launches += 5;
         return LQ_OK;
     }
     const int ne = (n + 1) & ~1, ld = ne | 1, half = ne / 2;
@@ -875,7 +913,7 @@ int svd_gram_local(Ctx* c, const double* A, long long m, int n, double tol, doub
     LQ_TRY(rk.alloc(c, 16));
     LQ_TRY(gram(c, A, m, n, G.as<double>()));                                  // svd.py:42
     if (sharded) LQ_TRY(comm_allreduce_sum(c, G.as<double>(), (long long)n * n));
-    LQ_TRY(eigh_jacobi(c, G.as<double>(), n, lam.as<double>(), V.as<double>())); // svd.py:46-51
+    LQ_TRY(eigh_jacobi(c, G.as<double>(), n, lam.as<double>(), V.as<double>(), true)); // svd.py:46-51 (G = A^T A is PSD)
     svd_post_kernel<<<small_grid(c, n), 256, sizeof(double) * n, c->stream>>>(lam.as<double>(), V.as<double>(), n, tol, s, M2.as<double>(), Vt,
                                                                              rk.as<int>());
     LQ_CHECK_LAUNCH(c);

@@ -740,3 +740,18 @@ def test_blocked_graph_replay_is_bitwise_identical(ctx):
     assert orc.qr_residual(A2, Q2, R2) <= RESID and orc.orth_error(Q2) <= ORTH
     for b in (dA, dQ, dR, dB, dQ2, dR2):
         b.free()
+
+
+def test_svd_direct_eigenvectors_and_replay_agree(ctx):
+    """For a well-conditioned Gram matrix (lambda_min > 1e-2 lambda_max) svd takes the eigenvectors as the normalised converged
+    Jacobi columns instead of replaying the rotation log; a matrix just outside that window replays.  Both must satisfy the
+    reference's contract (tests/test_svd.py:13-57: s vs LAPACK 1e-10, orthogonality, reconstruction) at the north-star
+    tolerances, for full n = 128 and a padded n."""
+    rng = np.random.default_rng(77)
+    for n, spread in ((128, 1.0), (128, 30.0), (100, 2.0), (37, 1.0)):
+        A = rng.standard_normal((6000, n)) * np.linspace(1.0, spread, n)[None, :]
+        U, s, Vt = lb.svd(A, ctx=ctx)
+        so = np.linalg.svd(A, compute_uv=False)
+        assert np.max(np.abs(s - so) / so) <= 1e-10, (n, spread)
+        assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12 and np.abs(Vt @ Vt.T - np.eye(n)).max() <= 1e-12, (n, spread)
+        assert np.linalg.norm((U * s) @ Vt - A) / np.linalg.norm(A) <= 1e-12, (n, spread)
